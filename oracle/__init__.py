@@ -1,0 +1,14 @@
+"""CPU oracle for the sameold receiver path — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may import this package.
+Nothing under sameold_b200/ does.
+"""
+from .pyoracle import (  # noqa: F401
+    Oracle,
+    OracleConfig,
+    OracleEvent,
+    build_oracle,
+    load_golden_recording,
+    GOLDEN_DIR,
+    EV_NAMES,
+)
