@@ -1,0 +1,651 @@
+// same_engine.cu — host side of the C ABI declared in include/same_engine.h.
+//
+// Responsibilities: configuration clamping (builder.rs setters), derivation of the receiver constants exactly as
+// SameReceiver::from does (receiver.rs:502-560; libm cosf/sinf/expf/sinhf on the host, bits uploaded to the device),
+// device memory for the resident per-stream state, double-buffered host->device sample copies overlapped with the
+// receiver kernel, and the event arena -> host hand-off.  There is no CPU decode path in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "same_params.h"
+
+extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps, const int16_t* d_samples,
+                                      const unsigned long long* d_offsets, const uint32_t* d_lengths,
+                                      cudaStream_t stream);
+extern "C" cudaError_t same_launch_init(const SameParams* p, const uint32_t* d_ids, uint32_t n, int after_reset,
+                                        cudaStream_t stream);
+
+namespace {
+
+thread_local std::string g_last_error;
+
+// Rust f32::clamp / min / max semantics for the builder setters
+inline float rclampf(float x, float lo, float hi) { if (x < lo) x = lo; if (x > hi) x = hi; return x; }
+
+constexpr float kMarkHz = 2083.3f;    // waveform.rs:6
+constexpr float kSpaceHz = 1562.5f;   // waveform.rs:9
+constexpr float kBaudHz = 520.83f;    // waveform.rs:12
+constexpr float kPi = 3.14159265358979323846f;  // std::f32::consts::PI
+
+// waveform.rs:54-64: h[i] = 2 * conj(exp(j*2*pi*f*(N-1-i))) / N, all in f32
+void cisoid_taps(uint32_t n, float freq_fs, float* re, float* im) {
+  for (uint32_t i = 0; i < n; ++i) {
+    float th = 2.0f * kPi * freq_fs * (float)(n - 1 - i);
+    float r = expf(0.0f);
+    float c = r * cosf(th), s = r * sinf(th);
+    re[i] = (2.0f * c) / (float)n;
+    im[i] = (2.0f * (-s)) / (float)n;
+  }
+}
+
+// symsync.rs:329-337
+void loop_alphabeta(float bw, float& alpha, float& beta) {
+  float w = 2.0f * kPi * bw;
+  float k0 = 2.0f, k1 = expf(-w), sh = sinhf(w);
+  alpha = k0 * k1 * sh;
+  beta = k0 * (1.0f - k1 * (sh + 1.0f));
+}
+
+size_t f32_as_usize(float x) {  // `as usize`: truncating, saturating, NaN -> 0
+  if (!(x > 0.0f)) return 0;
+  if (x >= 1.8e19f) return (size_t)-1;
+  return (size_t)x;
+}
+
+struct InputBuf {
+  int16_t* d = nullptr; size_t cap = 0;          // device samples
+  unsigned long long* d_off = nullptr; uint32_t* d_len = nullptr;
+  cudaEvent_t copied = nullptr, consumed = nullptr;
+  bool used = false;
+};
+
+}  // namespace
+
+struct same_engine {
+  same_config cfg;
+  int device = 0;
+  uint32_t n_streams = 0;
+  SameParams p;
+  SameTaps taps;
+  same_derived derived;
+  cudaStream_t compute = nullptr, copy = nullptr;
+  uint32_t* d_state = nullptr;
+  StreamBlob* d_blobs = nullptr;
+  same_event* d_events = nullptr;
+  uint8_t* d_payload = nullptr;
+  unsigned int* d_counters = nullptr;
+  unsigned int* h_counters = nullptr;   // pinned
+  same_soft_symbol* d_trace = nullptr;
+  uint32_t* d_ids = nullptr; size_t ids_cap = 0;
+  InputBuf in[2];
+  int cur = 0;
+  bool in_flight = false;
+  size_t events_cap = 0, payload_cap = 0;
+  std::vector<same_event> pend_events;
+  std::vector<uint8_t> pend_payload;
+  cudaEvent_t t_h2d0 = nullptr, t_h2d1 = nullptr, t_k0 = nullptr, t_k1 = nullptr, t_sw0 = nullptr, t_sw1 = nullptr;
+  bool timed_h2d = false, timed_kernel = false;
+  uint64_t launches = 0;
+  std::string last_error;
+};
+
+namespace {
+
+int fail(same_engine* e, int code, const std::string& msg) {
+  if (e) e->last_error = msg;
+  g_last_error = msg;
+  return code;
+}
+
+#define CK(e, call)                                                                                     \
+  do {                                                                                                  \
+    cudaError_t _err = (call);                                                                          \
+    if (_err != cudaSuccess)                                                                            \
+      return fail((e), SAME_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_err));            \
+  } while (0)
+
+int alloc_arenas(same_engine* e, size_t max_events, size_t max_payload) {
+  if (e->d_events) cudaFree(e->d_events);
+  if (e->d_payload) cudaFree(e->d_payload);
+  e->d_events = nullptr; e->d_payload = nullptr;
+  CK(e, cudaMalloc(&e->d_events, max_events * sizeof(same_event)));
+  CK(e, cudaMalloc(&e->d_payload, max_payload));
+  e->events_cap = max_events; e->payload_cap = max_payload;
+  e->p.events = e->d_events; e->p.payload = e->d_payload;
+  e->p.events_cap = (uint32_t)std::min<size_t>(max_events, 0xffffffffu);
+  e->p.payload_cap = (uint32_t)std::min<size_t>(max_payload, 0xffffffffu);
+  return SAME_OK;
+}
+
+// Pull the events produced since the last collect from the device arenas into the host pending lists.
+int collect(same_engine* e) {
+  CK(e, cudaMemcpyAsync(e->h_counters, e->d_counters, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, e->compute));
+  CK(e, cudaStreamSynchronize(e->compute));
+  const size_t nev = e->h_counters[0], npay = e->h_counters[1];
+  int rc = SAME_OK;
+  if (nev > e->events_cap || npay > e->payload_cap) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "event arena overflow: %zu events / %zu payload bytes produced, capacity %zu / %zu",
+             nev, npay, e->events_cap, e->payload_cap);
+    rc = fail(e, SAME_ERR_EVENT_OVERFLOW, buf);
+  }
+  const size_t cev = std::min(nev, e->events_cap), cpay = std::min(npay, e->payload_cap);
+  if (cev) {
+    const size_t base_ev = e->pend_events.size(), base_pay = e->pend_payload.size();
+    e->pend_events.resize(base_ev + cev);
+    e->pend_payload.resize(base_pay + cpay);
+    CK(e, cudaMemcpyAsync(e->pend_events.data() + base_ev, e->d_events, cev * sizeof(same_event),
+                          cudaMemcpyDeviceToHost, e->compute));
+    if (cpay)
+      CK(e, cudaMemcpyAsync(e->pend_payload.data() + base_pay, e->d_payload, cpay, cudaMemcpyDeviceToHost, e->compute));
+    CK(e, cudaStreamSynchronize(e->compute));
+    for (size_t i = base_ev; i < base_ev + cev; ++i) e->pend_events[i].data_offset += (uint32_t)base_pay;
+  }
+  CK(e, cudaMemsetAsync(e->d_counters, 0, 2 * sizeof(unsigned int), e->compute));
+  return rc;
+}
+
+int ensure_input(same_engine* e, InputBuf& b, size_t samples) {
+  if (samples > b.cap) {
+    if (b.d) CK(e, cudaFree(b.d));
+    b.d = nullptr; b.cap = 0;
+    size_t cap = samples + samples / 8 + 4096;
+    CK(e, cudaMalloc(&b.d, cap * sizeof(int16_t)));
+    b.cap = cap;
+  }
+  return SAME_OK;
+}
+
+int submit_common(same_engine* e, const int16_t* host_samples, const int16_t* dev_samples, uint64_t total,
+                  const uint64_t* offsets, const uint32_t* lengths, bool zeros) {
+  if (!e) return fail(nullptr, SAME_ERR_INVALID_ARG, "null engine");
+  if (!lengths || (!zeros && (!offsets || (!host_samples && !dev_samples && total))))
+    return fail(e, SAME_ERR_INVALID_ARG, "null argument");
+  CK(e, cudaSetDevice(e->device));
+  if (!zeros)
+    for (uint32_t i = 0; i < e->n_streams; ++i)
+      if (lengths[i] && offsets[i] + lengths[i] > total)
+        return fail(e, SAME_ERR_INVALID_ARG, "stream " + std::to_string(i) + ": offset+length exceeds total_samples");
+  for (uint32_t i = 0; i < e->n_streams; ++i)
+    if (lengths[i] > (1u << 30)) return fail(e, SAME_ERR_INVALID_ARG, "chunk longer than 2^30 samples");
+
+  InputBuf& b = e->in[e->cur];
+  e->cur ^= 1;
+  // the copy stream may only overwrite this buffer after the kernel that last read it has finished
+  if (b.used) CK(e, cudaStreamWaitEvent(e->copy, b.consumed, 0));
+  e->timed_h2d = false;
+  const int16_t* d_src = nullptr;
+  if (!zeros) {
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "offset type");
+    CK(e, cudaMemcpyAsync(b.d_off, offsets, e->n_streams * sizeof(uint64_t), cudaMemcpyHostToDevice, e->copy));
+  }
+  CK(e, cudaMemcpyAsync(b.d_len, lengths, e->n_streams * sizeof(uint32_t), cudaMemcpyHostToDevice, e->copy));
+  if (!zeros && host_samples) {
+    int rc = ensure_input(e, b, total);
+    if (rc) return rc;
+    CK(e, cudaEventRecord(e->t_h2d0, e->copy));
+    if (total) CK(e, cudaMemcpyAsync(b.d, host_samples, total * sizeof(int16_t), cudaMemcpyHostToDevice, e->copy));
+    CK(e, cudaEventRecord(e->t_h2d1, e->copy));
+    e->timed_h2d = true;
+    d_src = b.d;
+  } else if (!zeros) {
+    d_src = dev_samples;
+  }
+  CK(e, cudaEventRecord(b.copied, e->copy));
+  CK(e, cudaStreamWaitEvent(e->compute, b.copied, 0));
+  CK(e, cudaEventRecord(e->t_k0, e->compute));
+  CK(e, same_launch_rx(&e->p, &e->taps, d_src, b.d_off, b.d_len, e->compute));
+  CK(e, cudaEventRecord(e->t_k1, e->compute));
+  CK(e, cudaEventRecord(b.consumed, e->compute));
+  b.used = true;
+  e->timed_kernel = true;
+  e->launches += 1;
+  e->in_flight = true;
+  return SAME_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t same_abi_version(void) { return SAME_ABI_VERSION; }
+const char* same_last_error(void) { return g_last_error.c_str(); }
+const char* same_engine_last_error(const same_engine* e) { return e ? e->last_error.c_str() : g_last_error.c_str(); }
+
+void same_config_default(same_config* c, uint32_t input_rate) {  // builder.rs:50-67, 369-376
+  if (!c) return;
+  c->input_rate = input_rate;
+  c->dc_blocker_len = 0.38f;
+  c->agc_bandwidth = 0.01f;
+  c->agc_gain_min = 0.0f; c->agc_gain_max = 1.0e6f;
+  c->timing_bw_unlocked = 0.125f; c->timing_bw_locked = 0.05f;
+  c->timing_max_deviation = 0.01f;
+  c->squelch_power_open = 0.10f; c->squelch_power_close = 0.05f;
+  c->squelch_bandwidth = 0.125f;
+  c->preamble_max_errors = 2;
+  c->eq_enabled = 1; c->eq_nff = 6; c->eq_nfb = 4;
+  c->eq_relaxation = 0.05f; c->eq_regularization = 1.0e-6f;
+  c->frame_prefix_max_errors = 2; c->frame_max_invalid_bytes = 5;
+}
+
+void same_config_samedec(same_config* c, uint32_t input_rate) {  // crates/samedec/src/main.rs:29-37
+  if (!c) return;
+  same_config_default(c, input_rate);
+  c->agc_gain_min = 1.0f / (float)INT16_MAX;
+  c->agc_gain_max = 1.0f / 200.0f;
+}
+
+void same_config_sanitize(same_config* c) {  // the with_* setters, builder.rs:95-279, 393-425
+  if (!c) return;
+  c->dc_blocker_len = fmaxf(0.0f, c->dc_blocker_len);
+  c->agc_bandwidth = rclampf(c->agc_bandwidth, 0.0f, 1.0f);
+  c->timing_bw_unlocked = rclampf(c->timing_bw_unlocked, 0.0f, 1.0f);
+  c->timing_bw_locked = rclampf(c->timing_bw_locked, 0.0f, c->timing_bw_unlocked);
+  c->timing_max_deviation = rclampf(c->timing_max_deviation, 0.0f, 0.5f);
+  {
+    float open = c->squelch_power_open, close = c->squelch_power_close;
+    c->squelch_power_open = rclampf(open, 0.0f, 1.0f);
+    c->squelch_power_close = fminf(close, open);
+  }
+  c->frame_prefix_max_errors = std::min<uint32_t>(c->frame_prefix_max_errors, 7u);
+  c->eq_nff = std::max<uint32_t>(c->eq_nff, 1u);
+  c->eq_nfb = std::min<uint32_t>(std::max<uint32_t>(c->eq_nfb, 1u), c->eq_nff);
+  c->eq_relaxation = rclampf(c->eq_relaxation, 0.0f, 1.0f);
+  c->eq_regularization = rclampf(c->eq_regularization, 0.0f, 3.40282347e+38f);
+}
+
+int same_engine_create(const same_config* cfg_in, int device, uint32_t n_streams, same_engine** out) {
+  if (!cfg_in || !out) return fail(nullptr, SAME_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  if (n_streams == 0 || n_streams > (1u << 24)) return fail(nullptr, SAME_ERR_INVALID_ARG, "n_streams out of range");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, SAME_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(nullptr, SAME_ERR_NO_DEVICE, "device index out of range");
+
+  same_config cfg = *cfg_in;
+  same_config_sanitize(&cfg);
+  if (cfg.input_rate == 0) return fail(nullptr, SAME_ERR_INVALID_CONFIG, "input_rate must be > 0");
+
+  // ---- SameReceiver::from(&builder)  receiver.rs:502-560 ----
+  const float rate_f = (float)cfg.input_rate;
+  const float sps = rate_f / kBaudHz;                                         // waveform.rs:29-31
+  const size_t dc_len = f32_as_usize(cfg.dc_blocker_len * sps);               // receiver.rs:509
+  const size_t ntaps = f32_as_usize(floorf(sps));                             // waveform.rs:40
+  if (dc_len == 0) return fail(nullptr, SAME_ERR_INVALID_CONFIG, "DC blocker length is 0 samples (MovingAverage::new asserts len > 0, dcblock.rs:74)");
+  if (dc_len > SAME_MAX_DC) return fail(nullptr, SAME_ERR_INVALID_CONFIG, "DC blocker longer than the engine limit of 64 samples");
+  if (ntaps == 0 || ntaps > SAME_MAX_TAPS) return fail(nullptr, SAME_ERR_INVALID_CONFIG, "matched filter length outside 1..128 taps (input_rate 521..67186 Hz)");
+  uint32_t nff = cfg.eq_enabled ? cfg.eq_nff : 1u, nfb = cfg.eq_enabled ? cfg.eq_nfb : 1u;   // disabled_equalizer() receiver.rs:585-590
+  float relax = cfg.eq_enabled ? cfg.eq_relaxation : 0.0f;
+  float regul = cfg.eq_enabled ? cfg.eq_regularization : 1.0e-6f;
+  if (nff > SAME_MAX_EQ || nfb > SAME_MAX_EQ) return fail(nullptr, SAME_ERR_INVALID_CONFIG, "equalizer order beyond the engine limit of 16 taps per arm");
+
+  same_engine* e = new same_engine();
+  e->cfg = cfg; e->device = device; e->n_streams = n_streams;
+  SameParams& p = e->p;
+  memset(&p, 0, sizeof p);
+  memset(&e->taps, 0, sizeof e->taps);
+  p.n_streams = n_streams; p.input_rate = cfg.input_rate;
+  p.dc_len = (uint32_t)dc_len;
+  p.dc_inv_len = 1.0f / (float)dc_len;                                        // dcblock.rs:77
+  p.dc_gate = dc_len > 1 ? 1.0f : 0.0f;                                       // dcblock.rs:48
+  p.agc_bw = rclampf(cfg.agc_bandwidth * sps / rate_f, 0.0f, 1.0f);           // receiver.rs:511, agc.rs:51
+  p.agc_min = cfg.agc_gain_min; p.agc_max = cfg.agc_gain_max;
+  p.agc_gain0 = fminf(1.0f, cfg.agc_gain_min);                                // agc.rs:55
+  p.ntaps = (uint32_t)ntaps;
+  cisoid_taps(p.ntaps, kMarkHz / rate_f, e->taps.mark_re, e->taps.mark_im);   // waveform.rs:41-42
+  cisoid_taps(p.ntaps, kSpaceHz / rate_f, e->taps.space_re, e->taps.space_im);
+  p.spt = sps / 2.0f;                                                         // symsync.rs:146
+  {
+    float dev = sps * rclampf(cfg.timing_max_deviation, 0.0f, 0.5f);          // symsync.rs:147
+    p.pmin = p.spt - dev; p.pmax = p.spt + dev;
+  }
+  loop_alphabeta(cfg.timing_bw_unlocked, p.alpha_u, p.beta_u);
+  loop_alphabeta(cfg.timing_bw_locked, p.alpha_l, p.beta_l);
+  p.sq_sync_word = 0xabababab;                                                // waveform.rs:26
+  p.sq_max_err = cfg.preamble_max_errors;
+  p.sq_open = cfg.squelch_power_open;
+  p.sq_close = fminf(cfg.squelch_power_close, cfg.squelch_power_open);        // codesquelch.rs:199
+  p.sq_bw = rclampf(cfg.squelch_bandwidth, 0.0f, 1.0f);                       // codesquelch.rs:468
+  p.eq_nff = nff; p.eq_nfb = nfb; p.eq_relax = relax; p.eq_regul = regul;
+  p.fr_max_prefix_err = cfg.frame_prefix_max_errors; p.fr_max_invalid = cfg.frame_max_invalid_bytes;
+  {
+    float ib = (1.05f * kBaudHz) + 17.0f * 8.0f;                              // assembler.rs:85
+    p.interburst_symbols = (unsigned long long)ib;
+    p.history_symbols = 2ull * (p.interburst_symbols + 8ull * SAME_MAX_MESSAGE_LENGTH);  // assembler.rs:92-93
+    p.force_eom_samples = 135ull * (unsigned long long)cfg.input_rate;        // receiver.rs:496, 321-324
+  }
+  SameLayout& L = p.layout;
+  L.n_pad = (n_streams + 31u) & ~31u;
+  uint32_t w = F_NUM_SCALARS;
+  L.dc_ff = w; w += p.dc_len;
+  L.dc_fb = w; w += p.dc_len;
+  L.win = w; w += p.ntaps;
+  L.sqh = w; w += SAME_SQ_HIST;
+  L.eq_ffc = w; w += nff;
+  L.eq_fbc = w; w += nfb;
+  L.eq_ffw = w; w += nff;
+  L.eq_fbw = w; w += nfb;
+  L.n_words = w;
+
+  e->derived.sps = sps; e->derived.agc_bw = p.agc_bw; e->derived.agc_gain0 = p.agc_gain0;
+  e->derived.samples_per_ted = p.spt; e->derived.period_min = p.pmin; e->derived.period_max = p.pmax;
+  e->derived.alpha_unlocked = p.alpha_u; e->derived.beta_unlocked = p.beta_u;
+  e->derived.alpha_locked = p.alpha_l; e->derived.beta_locked = p.beta_l;
+  e->derived.dc_len = p.dc_len; e->derived.ntaps = p.ntaps;
+
+#define CKC(call)                                                                            \
+  do {                                                                                       \
+    cudaError_t _err = (call);                                                               \
+    if (_err != cudaSuccess) {                                                               \
+      int rc = fail(nullptr, SAME_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_err)); \
+      same_engine_destroy(e);                                                                \
+      return rc;                                                                             \
+    }                                                                                        \
+  } while (0)
+  CKC(cudaSetDevice(device));
+  CKC(cudaStreamCreateWithFlags(&e->compute, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
+  CKC(cudaMalloc(&e->d_state, (size_t)L.n_words * L.n_pad * sizeof(uint32_t)));
+  CKC(cudaMalloc(&e->d_blobs, (size_t)n_streams * sizeof(StreamBlob)));
+  CKC(cudaMemsetAsync(e->d_blobs, 0, (size_t)n_streams * sizeof(StreamBlob), e->compute));
+  CKC(cudaMalloc(&e->d_counters, 2 * sizeof(unsigned int)));
+  CKC(cudaMemsetAsync(e->d_counters, 0, 2 * sizeof(unsigned int), e->compute));
+  CKC(cudaHostAlloc(&e->h_counters, 2 * sizeof(unsigned int), cudaHostAllocDefault));
+  for (auto& b : e->in) {
+    CKC(cudaMalloc(&b.d_off, (size_t)n_streams * sizeof(unsigned long long)));
+    CKC(cudaMalloc(&b.d_len, (size_t)n_streams * sizeof(uint32_t)));
+    CKC(cudaEventCreateWithFlags(&b.copied, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&b.consumed, cudaEventDisableTiming));
+  }
+  CKC(cudaEventCreate(&e->t_h2d0)); CKC(cudaEventCreate(&e->t_h2d1));
+  CKC(cudaEventCreate(&e->t_k0)); CKC(cudaEventCreate(&e->t_k1));
+  CKC(cudaEventCreate(&e->t_sw0)); CKC(cudaEventCreate(&e->t_sw1));
+  p.state32 = e->d_state; p.blobs = e->d_blobs; p.counters = e->d_counters;
+  {
+    size_t nev = std::max<size_t>(65536, (size_t)n_streams * 64);
+    size_t npay = std::max<size_t>(4u << 20, (size_t)n_streams * 4096);
+    int rc = alloc_arenas(e, nev, npay);
+    if (rc) { same_engine_destroy(e); return rc; }
+  }
+  CKC(same_launch_init(&e->p, nullptr, n_streams, 0, e->compute));
+  CKC(cudaStreamSynchronize(e->compute));
+#undef CKC
+  *out = e;
+  return SAME_OK;
+}
+
+void same_engine_destroy(same_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->compute) cudaStreamSynchronize(e->compute);
+  if (e->copy) cudaStreamSynchronize(e->copy);
+  for (auto& b : e->in) {
+    if (b.d) cudaFree(b.d);
+    if (b.d_off) cudaFree(b.d_off);
+    if (b.d_len) cudaFree(b.d_len);
+    if (b.copied) cudaEventDestroy(b.copied);
+    if (b.consumed) cudaEventDestroy(b.consumed);
+  }
+  if (e->d_state) cudaFree(e->d_state);
+  if (e->d_blobs) cudaFree(e->d_blobs);
+  if (e->d_events) cudaFree(e->d_events);
+  if (e->d_payload) cudaFree(e->d_payload);
+  if (e->d_counters) cudaFree(e->d_counters);
+  if (e->h_counters) cudaFreeHost(e->h_counters);
+  if (e->d_trace) cudaFree(e->d_trace);
+  if (e->d_ids) cudaFree(e->d_ids);
+  for (cudaEvent_t ev : {e->t_h2d0, e->t_h2d1, e->t_k0, e->t_k1, e->t_sw0, e->t_sw1}) if (ev) cudaEventDestroy(ev);
+  if (e->compute) cudaStreamDestroy(e->compute);
+  if (e->copy) cudaStreamDestroy(e->copy);
+  delete e;
+}
+
+uint32_t same_engine_num_streams(const same_engine* e) { return e ? e->n_streams : 0; }
+uint32_t same_engine_input_rate(const same_engine* e) { return e ? e->cfg.input_rate : 0; }
+uint64_t same_engine_launch_count(const same_engine* e) { return e ? e->launches : 0; }
+void* same_engine_cuda_stream(same_engine* e) { return e ? (void*)e->compute : nullptr; }
+
+int same_engine_sync(same_engine* e) {
+  if (!e) return fail(nullptr, SAME_ERR_INVALID_ARG, "null engine");
+  CK(e, cudaSetDevice(e->device));
+  CK(e, cudaStreamSynchronize(e->copy));
+  CK(e, cudaStreamSynchronize(e->compute));
+  if (!e->in_flight) return SAME_OK;
+  e->in_flight = false;
+  return collect(e);
+}
+
+int same_engine_input_sample_counters(same_engine* e, uint64_t* out) {
+  if (!e || !out) return fail(e, SAME_ERR_INVALID_ARG, "null argument");
+  int rc = same_engine_sync(e);
+  if (rc) return rc;
+  const SameLayout& L = e->p.layout;
+  std::vector<uint32_t> lo(e->n_streams), hi(e->n_streams);
+  CK(e, cudaMemcpy(lo.data(), e->d_state + (size_t)F_N_LO * L.n_pad, e->n_streams * 4, cudaMemcpyDeviceToHost));
+  CK(e, cudaMemcpy(hi.data(), e->d_state + (size_t)F_N_HI * L.n_pad, e->n_streams * 4, cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < e->n_streams; ++i) out[i] = ((uint64_t)hi[i] << 32) | lo[i];
+  return SAME_OK;
+}
+
+int same_engine_reset(same_engine* e, const uint32_t* ids, uint32_t n) {
+  if (!e) return fail(nullptr, SAME_ERR_INVALID_ARG, "null engine");
+  int rc = same_engine_sync(e);
+  if (rc) return rc;
+  if (!ids) {
+    CK(e, same_launch_init(&e->p, nullptr, e->n_streams, 1, e->compute));
+    // SameReceiver::reset clears the event queue (receiver.rs:194)
+    e->pend_events.clear(); e->pend_payload.clear();
+  } else {
+    for (uint32_t i = 0; i < n; ++i)
+      if (ids[i] >= e->n_streams) return fail(e, SAME_ERR_INVALID_ARG, "stream id out of range");
+    if (n > e->ids_cap) {
+      if (e->d_ids) CK(e, cudaFree(e->d_ids));
+      e->d_ids = nullptr;
+      CK(e, cudaMalloc(&e->d_ids, (size_t)n * sizeof(uint32_t)));
+      e->ids_cap = n;
+    }
+    CK(e, cudaMemcpyAsync(e->d_ids, ids, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, e->compute));
+    CK(e, same_launch_init(&e->p, e->d_ids, n, 1, e->compute));
+    // drop queued events of the reset streams
+    std::vector<char> is_reset(e->n_streams, 0);
+    for (uint32_t i = 0; i < n; ++i) is_reset[ids[i]] = 1;
+    e->pend_events.erase(std::remove_if(e->pend_events.begin(), e->pend_events.end(),
+                                        [&](const same_event& ev) { return is_reset[ev.stream] != 0; }),
+                         e->pend_events.end());
+  }
+  if (e->d_trace) {
+    // trace fill counters live in the state and were zeroed by the init kernel
+  }
+  CK(e, cudaStreamSynchronize(e->compute));
+  return SAME_OK;
+}
+
+struct same_snapshot {
+  int device; uint32_t n_streams; size_t state_bytes, blob_bytes;
+  uint32_t* d_state; StreamBlob* d_blobs;
+};
+
+int same_engine_snapshot(same_engine* e, same_snapshot** out) {
+  if (!e || !out) return fail(e, SAME_ERR_INVALID_ARG, "null argument");
+  int rc = same_engine_sync(e);
+  if (rc) return rc;
+  same_snapshot* s = new same_snapshot();
+  s->device = e->device; s->n_streams = e->n_streams;
+  s->state_bytes = (size_t)e->p.layout.n_words * e->p.layout.n_pad * sizeof(uint32_t);
+  s->blob_bytes = (size_t)e->n_streams * sizeof(StreamBlob);
+  s->d_state = nullptr; s->d_blobs = nullptr;
+  cudaError_t err = cudaMalloc(&s->d_state, s->state_bytes);
+  if (err == cudaSuccess) err = cudaMalloc(&s->d_blobs, s->blob_bytes);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(s->d_state, e->d_state, s->state_bytes, cudaMemcpyDeviceToDevice, e->compute);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(s->d_blobs, e->d_blobs, s->blob_bytes, cudaMemcpyDeviceToDevice, e->compute);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->compute);
+  if (err != cudaSuccess) {
+    same_snapshot_free(s);
+    return fail(e, SAME_ERR_CUDA, std::string("snapshot: ") + cudaGetErrorString(err));
+  }
+  *out = s;
+  return SAME_OK;
+}
+
+int same_engine_restore(same_engine* e, const same_snapshot* s) {
+  if (!e || !s) return fail(e, SAME_ERR_INVALID_ARG, "null argument");
+  if (s->device != e->device || s->n_streams != e->n_streams ||
+      s->state_bytes != (size_t)e->p.layout.n_words * e->p.layout.n_pad * sizeof(uint32_t))
+    return fail(e, SAME_ERR_INVALID_ARG, "snapshot belongs to a different engine shape");
+  int rc = same_engine_sync(e);
+  if (rc) return rc;
+  CK(e, cudaMemcpyAsync(e->d_state, s->d_state, s->state_bytes, cudaMemcpyDeviceToDevice, e->compute));
+  CK(e, cudaMemcpyAsync(e->d_blobs, s->d_blobs, s->blob_bytes, cudaMemcpyDeviceToDevice, e->compute));
+  CK(e, cudaStreamSynchronize(e->compute));
+  e->pend_events.clear(); e->pend_payload.clear();
+  return SAME_OK;
+}
+
+void same_snapshot_free(same_snapshot* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->d_state) cudaFree(s->d_state);
+  if (s->d_blobs) cudaFree(s->d_blobs);
+  delete s;
+}
+
+int same_engine_set_event_capacity(same_engine* e, size_t max_events, size_t max_payload_bytes) {
+  if (!e || max_events == 0 || max_payload_bytes == 0) return fail(e, SAME_ERR_INVALID_ARG, "bad capacity");
+  int rc = same_engine_sync(e);
+  if (rc) return rc;
+  return alloc_arenas(e, max_events, max_payload_bytes);
+}
+
+int same_engine_submit_s16(same_engine* e, const int16_t* samples, uint64_t total_samples, const uint64_t* offsets,
+                           const uint32_t* lengths) {
+  return submit_common(e, samples, nullptr, total_samples, offsets, lengths, false);
+}
+
+int same_engine_submit_s16_device(same_engine* e, const int16_t* d_samples, uint64_t total_samples,
+                                  const uint64_t* offsets, const uint32_t* lengths) {
+  return submit_common(e, nullptr, d_samples, total_samples, offsets, lengths, false);
+}
+
+int same_engine_submit_zeros(same_engine* e, const uint32_t* lengths) {
+  return submit_common(e, nullptr, nullptr, 0, nullptr, lengths, true);
+}
+
+int same_engine_pending(same_engine* e, size_t* n_events, size_t* n_payload_bytes) {
+  if (!e) return fail(nullptr, SAME_ERR_INVALID_ARG, "null engine");
+  if (e->in_flight) { int rc = same_engine_sync(e); if (rc) return rc; }
+  if (n_events) *n_events = e->pend_events.size();
+  if (n_payload_bytes) *n_payload_bytes = e->pend_payload.size();
+  return SAME_OK;
+}
+
+int same_engine_drain_events(same_engine* e, same_event* events, size_t events_cap, size_t* n_events, uint8_t* payload,
+                             size_t payload_cap, size_t* n_payload) {
+  if (!e) return fail(nullptr, SAME_ERR_INVALID_ARG, "null engine");
+  if (e->in_flight) { int rc = same_engine_sync(e); if (rc) return rc; }
+  const size_t nev = e->pend_events.size(), npay = e->pend_payload.size();
+  if (n_events) *n_events = nev;
+  if (n_payload) *n_payload = npay;
+  if (nev > events_cap || npay > payload_cap || (nev && !events) || (npay && !payload))
+    return fail(e, SAME_ERR_INVALID_ARG, "drain buffers too small");
+  // per-stream order of occurrence, as iter_events yields them (receiver.rs:238-240, 267-269)
+  std::stable_sort(e->pend_events.begin(), e->pend_events.end(), [](const same_event& a, const same_event& b) {
+    return a.stream != b.stream ? a.stream < b.stream : a.seq < b.seq;
+  });
+  if (nev) memcpy(events, e->pend_events.data(), nev * sizeof(same_event));
+  if (npay) memcpy(payload, e->pend_payload.data(), npay);
+  e->pend_events.clear(); e->pend_payload.clear();
+  return SAME_OK;
+}
+
+int same_engine_enable_soft_trace(same_engine* e, uint32_t cap_per_stream) {
+  if (!e) return fail(nullptr, SAME_ERR_INVALID_ARG, "null engine");
+  int rc = same_engine_sync(e);
+  if (rc) return rc;
+  if (e->d_trace) { CK(e, cudaFree(e->d_trace)); e->d_trace = nullptr; }
+  e->p.trace = nullptr; e->p.trace_cap = 0;
+  const SameLayout& L = e->p.layout;
+  CK(e, cudaMemset(e->d_state + (size_t)F_TRACE_N * L.n_pad, 0, (size_t)L.n_pad * 4));
+  if (cap_per_stream) {
+    CK(e, cudaMalloc(&e->d_trace, (size_t)e->n_streams * cap_per_stream * sizeof(same_soft_symbol)));
+    e->p.trace = e->d_trace; e->p.trace_cap = cap_per_stream;
+  }
+  return SAME_OK;
+}
+
+int same_engine_read_soft_trace(same_engine* e, uint32_t stream, same_soft_symbol* out, size_t cap, size_t* n) {
+  if (!e || !n || stream >= e->n_streams) return fail(e, SAME_ERR_INVALID_ARG, "bad argument");
+  int rc = same_engine_sync(e);
+  if (rc) return rc;
+  *n = 0;
+  if (!e->d_trace) return SAME_OK;
+  const SameLayout& L = e->p.layout;
+  uint32_t fill = 0;
+  CK(e, cudaMemcpy(&fill, e->d_state + (size_t)F_TRACE_N * L.n_pad + stream, 4, cudaMemcpyDeviceToHost));
+  *n = fill;
+  if (out) {
+    size_t c = std::min<size_t>(fill, cap);
+    if (c) CK(e, cudaMemcpy(out, e->d_trace + (size_t)stream * e->p.trace_cap, c * sizeof(same_soft_symbol), cudaMemcpyDeviceToHost));
+    // reading rewinds this stream's trace
+    uint32_t zero = 0;
+    CK(e, cudaMemcpy(e->d_state + (size_t)F_TRACE_N * L.n_pad + stream, &zero, 4, cudaMemcpyHostToDevice));
+  }
+  return SAME_OK;
+}
+
+int same_engine_last_timing(same_engine* e, float* h2d_ms, float* kernel_ms) {
+  if (!e) return fail(nullptr, SAME_ERR_INVALID_ARG, "null engine");
+  if (e->in_flight) { int rc = same_engine_sync(e); if (rc) return rc; }
+  if (h2d_ms) { *h2d_ms = 0.0f; if (e->timed_h2d) CK(e, cudaEventElapsedTime(h2d_ms, e->t_h2d0, e->t_h2d1)); }
+  if (kernel_ms) { *kernel_ms = 0.0f; if (e->timed_kernel) CK(e, cudaEventElapsedTime(kernel_ms, e->t_k0, e->t_k1)); }
+  return SAME_OK;
+}
+
+int same_engine_timer_start(same_engine* e) {
+  if (!e) return fail(nullptr, SAME_ERR_INVALID_ARG, "null engine");
+  CK(e, cudaSetDevice(e->device));
+  // everything submitted later starts on the copy stream (offsets/lengths/samples), so the stopwatch starts there,
+  // after all earlier compute work
+  CK(e, cudaEventRecord(e->t_sw1, e->compute));
+  CK(e, cudaStreamWaitEvent(e->copy, e->t_sw1, 0));
+  CK(e, cudaEventRecord(e->t_sw0, e->copy));
+  return SAME_OK;
+}
+
+int same_engine_timer_stop(same_engine* e, float* elapsed_ms) {
+  if (!e || !elapsed_ms) return fail(e, SAME_ERR_INVALID_ARG, "null argument");
+  CK(e, cudaSetDevice(e->device));
+  CK(e, cudaStreamSynchronize(e->copy));
+  CK(e, cudaEventRecord(e->t_sw1, e->compute));
+  CK(e, cudaEventSynchronize(e->t_sw1));
+  CK(e, cudaEventElapsedTime(elapsed_ms, e->t_sw0, e->t_sw1));
+  return SAME_OK;
+}
+
+int same_engine_get_derived(const same_engine* e, same_derived* d, float* mark_re_im, float* space_re_im, size_t cap_taps) {
+  if (!e || !d) return SAME_ERR_INVALID_ARG;
+  *d = e->derived;
+  for (size_t i = 0; i < e->p.ntaps && i < cap_taps; ++i) {
+    if (mark_re_im) { mark_re_im[2 * i] = e->taps.mark_re[i]; mark_re_im[2 * i + 1] = e->taps.mark_im[i]; }
+    if (space_re_im) { space_re_im[2 * i] = e->taps.space_re[i]; space_re_im[2 * i + 1] = e->taps.space_im[i]; }
+  }
+  return SAME_OK;
+}
+
+void* same_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    g_last_error = "cudaHostAlloc failed";
+    return nullptr;
+  }
+  return p;
+}
+void same_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

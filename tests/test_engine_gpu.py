@@ -1,0 +1,328 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the CPU oracle on identical int16 inputs.
+
+Bar (BASELINE.json north_star): link + transport events bit-exact — kind, input_sample_counter, symbol count, burst /
+message bytes, parity and voting counts — and soft symbols bit-equal (the chain is chaotic: a tolerance would be
+meaningless; the 1e-4 relative tolerance of the north star is asserted as well).
+Nothing here reads /root/reference: recordings come from tests/golden/.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import sameold_b200 as sb
+from oracle import GOLDEN_DIR, Oracle, load_golden_recording
+from oracle.pyoracle import OracleConfig
+from sameold_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ["long_message", "npt", "two_and_two"]
+
+
+def _torch():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def oracle_cfg_from(builder) -> OracleConfig:
+    c, o = builder.config(), OracleConfig()
+    for name, _ in OracleConfig._fields_:
+        setattr(o, name, getattr(c, name))
+    return o
+
+
+def expected_lines(name):
+    with open(os.path.join(GOLDEN_DIR, f"{name}.22050.s16le.txt")) as f:
+        return [l.rstrip("\n") for l in f if not l.startswith("+OK")]
+
+
+def assert_events_equal(gpu_events, oracle_events, ctx=""):
+    g = [e.key() for e in gpu_events]
+    o = [e.key() for e in oracle_events]
+    if g != o:
+        for i, (a, b) in enumerate(zip(g, o)):
+            assert a == b, f"{ctx}: event {i} differs\n  gpu    {a}\n  oracle {b}"
+        assert len(g) == len(o), f"{ctx}: {len(g)} gpu events vs {len(o)} oracle events"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE config 2: the three sample/ recordings as one ragged 3-stream batch
+# ---------------------------------------------------------------------------------------------------------------------
+def test_golden_recordings_batch_bit_exact():
+    _torch()
+    recs = [load_golden_recording(n) for n in NAMES]
+    b = sb.SameReceiverBuilder.samedec(22050)
+    rx = b.build_batch(3)
+    rx.enable_soft_trace(16384)
+    evs = rx.process(recs)
+    traces = [rx.read_soft_trace(s) for s in range(3)]
+    tail = rx.flush_samedec()
+    for s, name in enumerate(NAMES):
+        o = Oracle(oracle_cfg_from(b))
+        o.enable_trace()
+        o.process_s16(recs[s])
+        n_before_flush = len(o.events())
+        ot = o.soft_trace()
+        o.flush_samedec()
+        oe = o.events()
+        assert_events_equal(evs[s], oe[:n_before_flush], f"{name} (input)")
+        assert_events_equal(evs[s] + tail[s], oe, f"{name} (input + EOF flush)")
+        # messages == the reference's golden stdout
+        msgs = [str(e.message_ok()) for e in evs[s] + tail[s] if e.message_ok() is not None]
+        assert msgs == expected_lines(name)
+        # soft symbols: bit-equal (and therefore within the stated 1e-4 relative tolerance)
+        t = traces[s]
+        assert len(t) == len(ot)
+        assert np.array_equal(t["sample"], ot["sample"])
+        assert np.array_equal(t["zero"].view(np.uint32), ot["zero"].view(np.uint32))
+        assert np.array_equal(t["sym"].view(np.uint32), ot["sym"].view(np.uint32))
+        assert np.allclose(t["sym"], ot["sym"], rtol=1e-4, atol=0)
+    assert np.array_equal(rx.input_sample_counters()[:3] >= np.array([len(r) for r in recs]), [True] * 3)
+
+
+def test_decode_samedec_matches_golden_text():
+    _torch()
+    rx = sb.SameReceiverBuilder.samedec(22050).build_batch(3)
+    out = rx.decode_samedec([load_golden_recording(n) for n in NAMES])
+    assert out == [expected_lines(n) for n in NAMES]
+
+
+def test_chunked_submit_equals_whole():
+    """State is resident between submits: arbitrary ragged chunking gives identical events (receiver.rs:233-274)."""
+    _torch()
+    recs = [load_golden_recording(n) for n in NAMES]
+    b = sb.SameReceiverBuilder.samedec(22050)
+    whole = b.build_batch(3).process(recs)
+    rx = b.build_batch(3)
+    rng = np.random.default_rng(7)
+    pos = [0, 0, 0]
+    got = [[], [], []]
+    while any(p < len(r) for p, r in zip(pos, recs)):
+        chunks = []
+        for s in range(3):
+            n = int(rng.integers(0, 60000)) if rng.random() > 0.1 else 0   # some streams skip a round
+            chunks.append(recs[s][pos[s]:pos[s] + n])
+            pos[s] += len(chunks[-1])
+        for s, e in enumerate(rx.process(chunks)):
+            got[s].extend(e)
+    for s in range(3):
+        assert_events_equal(got[s], whole[s], f"stream {s}")
+
+
+def test_tiny_chunks_cross_every_boundary():
+    """1..50-sample chunks: the sample clock, TED parity and byte clock all resume mid-period."""
+    _torch()
+    rec = load_golden_recording("npt")[:60000]
+    b = sb.SameReceiverBuilder.samedec(22050)
+    o = Oracle(oracle_cfg_from(b))
+    o.process_s16(rec)
+    rx = b.build_batch(1)
+    rng = np.random.default_rng(3)
+    got, i = [], 0
+    # first 3000 samples in tiny chunks, then the burst region in moderate chunks
+    while i < len(rec):
+        n = int(rng.integers(1, 50)) if i < 3000 else int(rng.integers(200, 5000))
+        got.extend(rx.process([rec[i:i + n]])[0])
+        i += n
+    assert_events_equal(got, o.events(), "tiny chunks")
+
+
+def test_library_default_config_and_event_order():
+    """Library defaults (AGC limits [0, 1e6], builder.rs:55) on a clean test burst: the event ORDER of the reference's
+    test_iter_events (receiver.rs:651-671) and bit-exact parity with the oracle."""
+    _torch()
+    plan = synth.StreamPlan("", [22050.0], [synth.PREAMBLE + b"ZCZC-EAS-DMO-372088-091724+0000-0001122-NOCALL00-"], 0.0, 1)
+    x = synth.render_numpy(plan, 5 * 22050, noise_sigma=0.0)
+    b = sb.SameReceiverBuilder(22050).with_timing_max_deviation(0.01)
+    evs = b.build_batch(1).process([x])[0]
+    o = Oracle(oracle_cfg_from(b))
+    o.process_s16(x)
+    assert_events_equal(evs, o.events(), "library defaults")
+    kinds = [e.kind for e in evs]
+    assert kinds == [1, 2, 3, 17, 0], kinds  # Searching, Reading, Burst, Assembling, NoCarrier
+    assert evs[2].data.startswith(b"ZCZC-EAS-DMO-372088-091724+0000-0001122-NOCALL00-")
+
+
+def test_derived_constants_bit_equal():
+    _torch()
+    for rate in (22050, 44100, 48000, 11025):
+        b = sb.SameReceiverBuilder.samedec(rate)
+        d = b.build_batch(1).derived()
+        o = Oracle.derived(oracle_cfg_from(b))
+        for k, v in o.items():
+            if isinstance(v, np.ndarray):
+                assert np.array_equal(d[k].view(np.uint32), v.view(np.uint32)), (rate, k)
+            elif isinstance(v, float):
+                assert np.float32(d[k]).view(np.uint32) == np.float32(v).view(np.uint32), (rate, k)
+            else:
+                assert d[k] == v, (rate, k)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE config 3 (scaled to what the oracle finishes in seconds): device-generated synthetic corpus
+# ---------------------------------------------------------------------------------------------------------------------
+def _device_corpus(n_streams, seconds, rate=22050, first=0):
+    torch = _torch()
+    n = int(seconds * rate)
+    stride = (n + 7) // 8 * 8
+    buf = torch.empty((n_streams, stride), dtype=torch.int16, device="cuda")
+    plans = synth.plan_corpus(n_streams, rate, seconds, first_stream=first)
+    synth.generate_on_device(plans, buf.data_ptr(), stride, n, rate)
+    return buf, plans, n, stride
+
+
+def test_synthetic_corpus_bit_exact_vs_oracle():
+    _torch()
+    ns, secs = 96, 45.0      # 3 warps, ragged tail warp excluded on purpose below
+    buf, plans, n, stride = _device_corpus(ns, secs)
+    host = buf.cpu().numpy()
+    b = sb.SameReceiverBuilder.samedec(22050)
+    rx = b.build_batch(ns)
+    offsets = np.arange(ns, dtype=np.uint64) * np.uint64(stride)
+    rx.submit_device(buf.data_ptr(), ns * stride, offsets, np.full(ns, n, np.uint32))
+    rx.sync()
+    evs = rx.drain_by_stream()
+    decoded = 0
+    for s in range(ns):
+        o = Oracle(oracle_cfg_from(b))
+        o.process_s16(host[s, :n])
+        assert_events_equal(evs[s], o.events(), f"synthetic stream {s}")
+        msgs = [str(e.message_ok()) for e in evs[s] if e.message_ok() is not None]
+        if plans[s].header in msgs:
+            decoded += 1
+    # the corpus is decodable: at 10 dB SNR nearly every header comes through
+    assert decoded >= int(0.9 * ns), decoded
+
+
+def test_device_and_host_submit_agree_and_ragged_lengths():
+    _torch()
+    ns = 40                  # not a multiple of 32: exercises the padded lanes
+    buf, plans, n, stride = _device_corpus(ns, 12.0, first=1000)
+    host = buf.cpu().numpy()
+    lengths = np.array([n - 997 * (s % 7) for s in range(ns)], np.uint32)
+    lengths[5] = 0           # a stream that receives nothing
+    lengths[6] = 1
+    b = sb.SameReceiverBuilder.samedec(22050)
+    rx_d = b.build_batch(ns)
+    offsets = np.arange(ns, dtype=np.uint64) * np.uint64(stride)
+    rx_d.submit_device(buf.data_ptr(), ns * stride, offsets, lengths)
+    rx_d.sync()
+    ev_d = rx_d.drain_by_stream()
+    rx_h = b.build_batch(ns)
+    ev_h = rx_h.process([host[s, :lengths[s]] for s in range(ns)])
+    assert np.array_equal(rx_d.input_sample_counters(), lengths.astype(np.uint64))
+    for s in range(ns):
+        assert_events_equal(ev_d[s], ev_h[s], f"stream {s} device vs host submit")
+        o = Oracle(oracle_cfg_from(b))
+        o.process_s16(host[s, :lengths[s]])
+        assert_events_equal(ev_h[s], o.events(), f"stream {s}")
+
+
+def test_other_sample_rates_generic_kernel():
+    """44.1 kHz (84 taps, DC length 32) and 48 kHz (92 taps, DC length 35: the DC blocker is no longer exact in f32 and
+    must be evaluated sequentially in the reference's order) — SURVEY.md §8f N4."""
+    _torch()
+    for rate in (44100, 48000, 11025):
+        plan = synth.plan_stream(77, rate, 30.0)
+        x = synth.render_numpy(plan, int(30 * rate), rate)
+        b = sb.SameReceiverBuilder.samedec(rate)
+        evs = b.build_batch(1).process([x])[0]
+        o = Oracle(oracle_cfg_from(b))
+        o.process_s16(x)
+        assert_events_equal(evs, o.events(), f"rate {rate}")
+        assert any(e.kind == 3 for e in evs), f"no burst decoded at {rate} Hz"
+
+
+def test_non_default_configs():
+    _torch()
+    x = load_golden_recording("two_and_two")
+    variants = [
+        sb.SameReceiverBuilder.samedec(22050).without_adaptive_equalizer(),
+        sb.SameReceiverBuilder.samedec(22050).with_adaptive_equalizer(sb.EqualizerBuilder().with_filter_order(8, 3).with_relaxation(0.1)),
+        sb.SameReceiverBuilder.samedec(22050).with_timing_bandwidth(0.2, 0.02).with_preamble_max_errors(4).with_squelch_power(0.2, 0.1),
+        sb.SameReceiverBuilder(22050).with_dc_blocker_length(0.03).with_frame_max_invalid(0).with_frame_prefix_max_errors(0),
+    ]
+    for i, b in enumerate(variants):
+        evs = b.build_batch(1).process([x])[0]
+        o = Oracle(oracle_cfg_from(b))
+        o.process_s16(x)
+        assert_events_equal(evs, o.events(), f"variant {i}")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Boundary behaviour
+# ---------------------------------------------------------------------------------------------------------------------
+def test_empty_and_reset_and_errors():
+    _torch()
+    b = sb.SameReceiverBuilder.samedec(22050)
+    rx = b.build_batch(2)
+    assert rx.process([np.zeros(0, np.int16), None]) == [[], []]
+    assert list(rx.input_sample_counters()) == [0, 0]
+    rec = load_golden_recording("npt")
+    first = rx.process([rec, rec[:50000]])
+    # reset stream 0 only: it starts over with AGC gain 1.0 (agc.rs:61), stream 1 keeps going
+    rx.reset([0])
+    assert list(rx.input_sample_counters()) == [0, 50000]
+    second = rx.process([rec, rec[50000:]])
+    o = Oracle(oracle_cfg_from(b))
+    o.process_s16(rec)
+    assert_events_equal(first[0], o.events(), "stream 0 first pass")
+    assert_events_equal(first[1] + second[1], o.events(), "stream 1 across the reset of stream 0")
+    o.reset()
+    o.process_s16(rec)
+    assert_events_equal(second[0], o.events(), "stream 0 after reset()")
+    # invalid configurations are rejected like the reference's panics
+    with pytest.raises(sb.SameEngineError) as ei:
+        sb.SameReceiverBuilder(22050).with_dc_blocker_length(0.0).build_batch(1)
+    assert ei.value.code == 2
+    with pytest.raises(ValueError):
+        rx.submit([rec])
+
+
+def test_single_stream_facade_and_flush():
+    """SameReceiver.iter_messages / flush (receiver.rs:155-161, 216-224), incl. the forced EOM after 135 s."""
+    _torch()
+    rec = load_golden_recording("long_message")
+    rx = sb.SameReceiverBuilder.samedec(22050).build()
+    assert rx.input_rate() == 22050
+    assert list(rx.iter_messages(rec)) == []          # the header is still pending at EOF
+    m = rx.flush()
+    assert m is not None and m.is_start and str(m) == expected_lines("long_message")[0]
+    assert m.voting_byte_count == 252 and m.parity_error_count == 0
+    # flush() stopped AT the message sample, exactly like the reference
+    o = Oracle.samedec()
+    o.process_s16(rec)
+    o.flush_samedec()
+    som = [e for e in o.events() if e.kind == 18][0]
+    assert rx.input_sample_counter() == som.sample
+    assert rx.flush() is None                          # next 4 s of zeros: nothing
+    # 135 s of silence later the receiver forces an EndOfMessage (receiver.rs:300-309)
+    msgs = list(rx.iter_messages(np.zeros(136 * 22050, np.int16)))
+    assert [str(x) for x in msgs] == ["NNNN"]
+    rx.reset()
+    assert rx.input_sample_counter() == 0
+
+
+def test_snapshot_restore_is_clone():
+    _torch()
+    rec = load_golden_recording("two_and_two")
+    rx = sb.SameReceiverBuilder.samedec(22050).build_batch(1)
+    a = rx.process([rec[:80000]])[0]
+    snap = rx.snapshot()
+    b1 = rx.process([rec[80000:]])[0]
+    rx.restore(snap)
+    b2 = rx.process([rec[80000:]])[0]
+    rx.free_snapshot(snap)
+    assert_events_equal(b1, b2, "after restore")
+    assert len(a) + len(b1) > 10
+
+
+def test_event_overflow_is_reported():
+    _torch()
+    rx = sb.SameReceiverBuilder.samedec(22050).build_batch(1)
+    rx.set_event_capacity(2, 16)
+    with pytest.raises(sb.SameEngineError) as ei:
+        rx.process([load_golden_recording("npt")])
+    assert ei.value.code == 5
