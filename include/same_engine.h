@@ -146,6 +146,12 @@ int same_engine_set_event_capacity(same_engine* e, size_t max_events, size_t max
  * host->device copy and the kernels; the caller keeps `samples` alive until same_engine_sync returns. */
 int same_engine_submit_s16(same_engine* e, const int16_t* samples, uint64_t total_samples, const uint64_t* offsets,
                            const uint32_t* lengths);
+/* The natural batched layout: a HOST matrix samples[n_streams][row_stride] (int16).  Feeds columns
+ * [col_start, col_start + n_cols) of every row, i.e. the same time slice of every stream, with one strided
+ * host->device copy (cudaMemcpy2DAsync).  Successive calls with advancing col_start stream a long recording through the
+ * engine in time-chunks; the copy of chunk k+1 overlaps the kernel of chunk k (two device buffers, two CUDA streams). */
+int same_engine_submit_s16_2d(same_engine* e, const int16_t* samples, uint64_t row_stride, uint64_t col_start,
+                              uint32_t n_cols);
 /* Same, but `d_samples` already lives in this device's memory (no copy). */
 int same_engine_submit_s16_device(same_engine* e, const int16_t* d_samples, uint64_t total_samples,
                                   const uint64_t* offsets, const uint32_t* lengths);

@@ -74,6 +74,7 @@ API = {
     "same_snapshot_free": (None, [_P]),
     "same_engine_set_event_capacity": (C.c_int, [_P, C.c_size_t, C.c_size_t]),
     "same_engine_submit_s16": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
+    "same_engine_submit_s16_2d": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint32]),
     "same_engine_submit_s16_device": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
     "same_engine_submit_zeros": (C.c_int, [_P, _P]),
     "same_engine_sync": (C.c_int, [_P]),

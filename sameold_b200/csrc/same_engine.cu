@@ -162,11 +162,24 @@ int ensure_input(same_engine* e, InputBuf& b, size_t samples) {
   return SAME_OK;
 }
 
+struct Submit2D { uint64_t row_stride = 0, col_start = 0; uint32_t n_cols = 0; bool on = false; };
+
 int submit_common(same_engine* e, const int16_t* host_samples, const int16_t* dev_samples, uint64_t total,
-                  const uint64_t* offsets, const uint32_t* lengths, bool zeros) {
+                  const uint64_t* offsets, const uint32_t* lengths, bool zeros, Submit2D two_d = Submit2D()) {
   if (!e) return fail(nullptr, SAME_ERR_INVALID_ARG, "null engine");
+  std::vector<uint64_t> off2d;
+  std::vector<uint32_t> len2d;
+  if (two_d.on) {
+    if (!host_samples) return fail(e, SAME_ERR_INVALID_ARG, "null argument");
+    if (two_d.col_start + two_d.n_cols > two_d.row_stride) return fail(e, SAME_ERR_INVALID_ARG, "column range exceeds row_stride");
+    off2d.resize(e->n_streams); len2d.assign(e->n_streams, two_d.n_cols);
+    for (uint32_t i = 0; i < e->n_streams; ++i) off2d[i] = (uint64_t)i * two_d.n_cols;
+    offsets = off2d.data(); lengths = len2d.data();
+    total = (uint64_t)e->n_streams * two_d.n_cols;
+  }
   if (!lengths || (!zeros && (!offsets || (!host_samples && !dev_samples && total))))
     return fail(e, SAME_ERR_INVALID_ARG, "null argument");
+  if (two_d.on && two_d.n_cols > (1u << 30)) return fail(e, SAME_ERR_INVALID_ARG, "chunk longer than 2^30 samples");
   CK(e, cudaSetDevice(e->device));
   if (!zeros)
     for (uint32_t i = 0; i < e->n_streams; ++i)
@@ -190,7 +203,12 @@ int submit_common(same_engine* e, const int16_t* host_samples, const int16_t* de
     int rc = ensure_input(e, b, total);
     if (rc) return rc;
     CK(e, cudaEventRecord(e->t_h2d0, e->copy));
-    if (total) CK(e, cudaMemcpyAsync(b.d, host_samples, total * sizeof(int16_t), cudaMemcpyHostToDevice, e->copy));
+    if (total && two_d.on)
+      CK(e, cudaMemcpy2DAsync(b.d, (size_t)two_d.n_cols * sizeof(int16_t), host_samples + two_d.col_start,
+                              (size_t)two_d.row_stride * sizeof(int16_t), (size_t)two_d.n_cols * sizeof(int16_t),
+                              e->n_streams, cudaMemcpyHostToDevice, e->copy));
+    else if (total)
+      CK(e, cudaMemcpyAsync(b.d, host_samples, total * sizeof(int16_t), cudaMemcpyHostToDevice, e->copy));
     CK(e, cudaEventRecord(e->t_h2d1, e->copy));
     e->timed_h2d = true;
     d_src = b.d;
@@ -440,6 +458,7 @@ int same_engine_reset(same_engine* e, const uint32_t* ids, uint32_t n) {
   if (rc) return rc;
   if (!ids) {
     CK(e, same_launch_init(&e->p, nullptr, e->n_streams, 1, e->compute));
+    e->launches += 1;
     // SameReceiver::reset clears the event queue (receiver.rs:194)
     e->pend_events.clear(); e->pend_payload.clear();
   } else {
@@ -453,6 +472,7 @@ int same_engine_reset(same_engine* e, const uint32_t* ids, uint32_t n) {
     }
     CK(e, cudaMemcpyAsync(e->d_ids, ids, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, e->compute));
     CK(e, same_launch_init(&e->p, e->d_ids, n, 1, e->compute));
+    e->launches += 1;
     // drop queued events of the reset streams
     std::vector<char> is_reset(e->n_streams, 0);
     for (uint32_t i = 0; i < n; ++i) is_reset[ids[i]] = 1;
@@ -526,6 +546,12 @@ int same_engine_set_event_capacity(same_engine* e, size_t max_events, size_t max
 int same_engine_submit_s16(same_engine* e, const int16_t* samples, uint64_t total_samples, const uint64_t* offsets,
                            const uint32_t* lengths) {
   return submit_common(e, samples, nullptr, total_samples, offsets, lengths, false);
+}
+
+int same_engine_submit_s16_2d(same_engine* e, const int16_t* samples, uint64_t row_stride, uint64_t col_start,
+                              uint32_t n_cols) {
+  Submit2D t; t.row_stride = row_stride; t.col_start = col_start; t.n_cols = n_cols; t.on = true;
+  return submit_common(e, samples, nullptr, 0, nullptr, nullptr, false, t);
 }
 
 int same_engine_submit_s16_device(same_engine* e, const int16_t* d_samples, uint64_t total_samples,

@@ -348,6 +348,11 @@ class SameBatchReceiver:
         self._keep = (flat, offsets, lengths)
         self._ck(self._lib.same_engine_submit_s16(self._h, flat.ctypes.data, flat.size, offsets.ctypes.data, lengths.ctypes.data))
 
+    def submit_2d(self, host_ptr: int, row_stride: int, col_start: int, n_cols: int):
+        """Time slice [col_start, col_start+n_cols) of a host matrix int16[n_streams][row_stride] (raw host pointer,
+        ideally pinned memory from same_host_alloc): one strided copy, overlapped with the previous chunk's kernel."""
+        self._ck(self._lib.same_engine_submit_s16_2d(self._h, C.c_void_p(host_ptr), int(row_stride), int(col_start), int(n_cols)))
+
     def submit_device(self, d_ptr: int, total_samples: int, offsets: np.ndarray, lengths: np.ndarray):
         """Samples already resident in this device's memory (raw device pointer, e.g. torch_tensor.data_ptr())."""
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
