@@ -174,6 +174,10 @@ int same_engine_drain_events(same_engine* e, same_event* events, size_t events_c
 int same_engine_enable_soft_trace(same_engine* e, uint32_t cap_per_stream);
 int same_engine_read_soft_trace(same_engine* e, uint32_t stream, same_soft_symbol* out, size_t cap, size_t* n);
 
+/* Engine options.  "force_generic" = 1 runs the rate-generic kernel even where the 22050 Hz fast kernel applies (both
+ * must produce identical results; used by the tests to cross-check them).  Implies sync. */
+int same_engine_set_option(same_engine* e, const char* key, int value);
+
 /* Timing of the last completed submit, measured with CUDA events on the engine's stream: host->device copy and
  * receiver kernel, in milliseconds; kernel launch count since create (for bench.py's gpu_launches). */
 int same_engine_last_timing(same_engine* e, float* h2d_ms, float* kernel_ms);

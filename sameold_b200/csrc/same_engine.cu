@@ -10,14 +10,15 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
 #include "same_params.h"
 
-extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps, const int16_t* d_samples,
-                                      const unsigned long long* d_offsets, const uint32_t* d_lengths,
-                                      cudaStream_t stream);
+extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps, const SameTaps2* taps2, int force_generic,
+                                      const int16_t* d_samples, const unsigned long long* d_offsets,
+                                      const uint32_t* d_lengths, cudaStream_t stream);
 extern "C" cudaError_t same_launch_init(const SameParams* p, const uint32_t* d_ids, uint32_t n, int after_reset,
                                         cudaStream_t stream);
 
@@ -73,6 +74,8 @@ struct same_engine {
   uint32_t n_streams = 0;
   SameParams p;
   SameTaps taps;
+  SameTaps2 taps2;
+  int force_generic = 0;
   same_derived derived;
   cudaStream_t compute = nullptr, copy = nullptr;
   uint32_t* d_state = nullptr;
@@ -218,7 +221,7 @@ int submit_common(same_engine* e, const int16_t* host_samples, const int16_t* de
   CK(e, cudaEventRecord(b.copied, e->copy));
   CK(e, cudaStreamWaitEvent(e->compute, b.copied, 0));
   CK(e, cudaEventRecord(e->t_k0, e->compute));
-  CK(e, same_launch_rx(&e->p, &e->taps, d_src, b.d_off, b.d_len, e->compute));
+  CK(e, same_launch_rx(&e->p, &e->taps, &e->taps2, e->force_generic, d_src, b.d_off, b.d_len, e->compute));
   CK(e, cudaEventRecord(e->t_k1, e->compute));
   CK(e, cudaEventRecord(b.consumed, e->compute));
   b.used = true;
@@ -290,6 +293,8 @@ int same_engine_create(const same_config* cfg_in, int device, uint32_t n_streams
   same_config cfg = *cfg_in;
   same_config_sanitize(&cfg);
   if (cfg.input_rate == 0) return fail(nullptr, SAME_ERR_INVALID_CONFIG, "input_rate must be > 0");
+  if (!(cfg.agc_gain_min <= cfg.agc_gain_max))  // f32::clamp panics when min > max or either is NaN (agc.rs:75)
+    return fail(nullptr, SAME_ERR_INVALID_CONFIG, "agc_gain_min must be <= agc_gain_max");
 
   // ---- SameReceiver::from(&builder)  receiver.rs:502-560 ----
   const float rate_f = (float)cfg.input_rate;
@@ -319,6 +324,13 @@ int same_engine_create(const same_config* cfg_in, int device, uint32_t n_streams
   p.ntaps = (uint32_t)ntaps;
   cisoid_taps(p.ntaps, kMarkHz / rate_f, e->taps.mark_re, e->taps.mark_im);   // waveform.rs:41-42
   cisoid_taps(p.ntaps, kSpaceHz / rate_f, e->taps.space_re, e->taps.space_im);
+  memset(&e->taps2, 0, sizeof e->taps2);
+  for (uint32_t i = 0; i < p.ntaps && i < 64; ++i) {
+    e->taps2.mark[i] = make_float2(e->taps.mark_re[i], e->taps.mark_im[i]);
+    e->taps2.space[i] = make_float2(e->taps.space_re[i], e->taps.space_im[i]);
+  }
+  p.f_one = 1.0f; p.f_negzero = -0.0f;
+  if (const char* fg = getenv("SAME_FORCE_GENERIC")) e->force_generic = atoi(fg);
   p.spt = sps / 2.0f;                                                         // symsync.rs:146
   {
     float dev = sps * rclampf(cfg.timing_max_deviation, 0.0f, 0.5f);          // symsync.rs:147
@@ -623,6 +635,14 @@ int same_engine_read_soft_trace(same_engine* e, uint32_t stream, same_soft_symbo
     CK(e, cudaMemcpy(e->d_state + (size_t)F_TRACE_N * L.n_pad + stream, &zero, 4, cudaMemcpyHostToDevice));
   }
   return SAME_OK;
+}
+
+int same_engine_set_option(same_engine* e, const char* key, int value) {
+  if (!e || !key) return fail(e, SAME_ERR_INVALID_ARG, "null argument");
+  int rc = same_engine_sync(e);
+  if (rc) return rc;
+  if (strcmp(key, "force_generic") == 0) { e->force_generic = value; return SAME_OK; }
+  return fail(e, SAME_ERR_INVALID_ARG, std::string("unknown option ") + key);
 }
 
 int same_engine_last_timing(same_engine* e, float* h2d_ms, float* kernel_ms) {

@@ -10,6 +10,8 @@
 
 #include <stdint.h>
 
+#include <vector_types.h>
+
 #include "../../include/same_engine.h"
 
 #define SAME_MAX_TAPS 128      // matched filter taps (floor(rate/520.83)): 42 @22050, 84 @44100, 92 @48000
@@ -42,6 +44,7 @@ enum SameField {
   F_SEQ,          // per-stream event sequence number
   F_TRACE_N,      // soft-trace fill
   F_DC_FFSUM, F_DC_FBSUM,  // MovingAverage::moving_sum       dcblock.rs:65
+  F_SQ_HEAD,      // next write slot (== oldest entry) of the in-place squelch history ring `sqh`
   F_NUM_SCALARS
 };
 
@@ -63,7 +66,7 @@ struct SameLayout {
   uint32_t dc_ff;       // [dc_len]  ff MovingAverage window, oldest first
   uint32_t dc_fb;       // [dc_len]
   uint32_t win;         // [ntaps]   FskDemod window, oldest first
-  uint32_t sqh;         // [64]      squelch sample history, oldest first (valid: min(64, 2*symcount))
+  uint32_t sqh;         // [64]      squelch sample history, ring in place: oldest entry at slot F_SQ_HEAD
   uint32_t eq_ffc, eq_fbc, eq_ffw, eq_fbw;  // equalizer taps and windows (windows oldest first)
   uint32_t n_words;     // total words per stream
 };
@@ -126,6 +129,14 @@ struct SameParams {
   // per-stream state
   uint32_t* state32;
   StreamBlob* blobs;
+  // 1.0f and -0.0f as RUN-TIME values: fma(a, f_one, b) and fma(a, b, f_negzero) are the exact add / exact multiply of
+  // the packed FFMA2 path; as compile-time constants ptxas would fold them and re-fuse the pair (it contracts packed
+  // mul+add even with --fmad=false)
+  float f_one, f_negzero;
+};
+
+struct SameTaps2 {                // the same taps as (re, im) pairs for the packed-FFMA2 matched filter
+  float2 mark[64], space[64];
 };
 
 struct SameTaps {                 // matched filter taps, tap i pairs with the sample i steps back from the newest

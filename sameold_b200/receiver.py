@@ -388,6 +388,23 @@ class SameBatchReceiver:
                                          e.voting_bytes, e.flags))
         return out
 
+    EVENT_DTYPE = np.dtype([("stream", "<u4"), ("seq", "<u4"), ("sample", "<u8"), ("symbol_count", "<u8"),
+                            ("kind", "<u4"), ("err", "<u4"), ("data_offset", "<u4"), ("data_len", "<u4"),
+                            ("parity_errors", "<u2"), ("voting_bytes", "<u2"), ("flags", "<u4")])
+
+    def drain_raw(self):
+        """All pending events as a numpy structured array (same_event records, sorted by stream then occurrence) plus
+        the payload arena — no per-event Python objects (what a high-rate consumer uses)."""
+        nev, npay = C.c_size_t(), C.c_size_t()
+        self._ck(self._lib.same_engine_pending(self._h, C.byref(nev), C.byref(npay)))
+        self._keep = None
+        evs = np.zeros(nev.value, self.EVENT_DTYPE)
+        pay = np.zeros(max(npay.value, 1), np.uint8)
+        if nev.value:
+            self._ck(self._lib.same_engine_drain_events(self._h, evs.ctypes.data, nev.value, C.byref(nev), pay.ctypes.data,
+                                                        pay.size, C.byref(npay)))
+        return evs, pay[: npay.value]
+
     def drain_by_stream(self) -> List[List[SameReceiverEvent]]:
         out: List[List[SameReceiverEvent]] = [[] for _ in range(self.n_streams)]
         for e in self.drain():
@@ -457,6 +474,9 @@ class SameBatchReceiver:
         self._ck(self._lib.same_engine_read_soft_trace(self._h, stream, arr, n.value, C.byref(n)))
         a = np.frombuffer(arr, dtype=np.dtype([("sample", "<u8"), ("zero", "<f4"), ("sym", "<f4")]))[: n.value]
         return a.copy()
+
+    def set_option(self, key: str, value: int):
+        self._ck(self._lib.same_engine_set_option(self._h, key.encode(), int(value)))
 
     def last_timing(self):
         h2d, k = C.c_float(), C.c_float()

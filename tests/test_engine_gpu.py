@@ -220,6 +220,38 @@ def test_device_and_host_submit_agree_and_ragged_lengths():
         assert_events_equal(ev_h[s], o.events(), f"stream {s}")
 
 
+def test_fast_and_generic_kernels_agree():
+    """The 22050 Hz fast kernel (integer DC blocker, packed FFMA2 matched filter, 16-byte loads) and the rate-generic
+    kernel (literal f32 recursion) must give identical events AND identical resident state: chunks alternate between
+    the two kernels mid-stream, with ragged, odd and unaligned chunk lengths."""
+    _torch()
+    recs = [load_golden_recording(n) for n in NAMES] + [synth.render_numpy(synth.plan_stream(5, seconds=20.0), 20 * 22050)]
+    b = sb.SameReceiverBuilder.samedec(22050)
+    ref = b.build_batch(len(recs))
+    ref.set_option("force_generic", 1)
+    want = ref.process(recs)
+    rx = b.build_batch(len(recs))
+    rng = np.random.default_rng(11)
+    pos = [0] * len(recs)
+    got = [[] for _ in recs]
+    k = 0
+    while any(p < len(r) for p, r in zip(pos, recs)):
+        rx.set_option("force_generic", k % 2)
+        k += 1
+        chunks = []
+        for s_ in range(len(recs)):
+            n = int(rng.integers(1, 40000))
+            chunks.append(recs[s_][pos[s_]:pos[s_] + n])
+            pos[s_] += len(chunks[-1])
+        for s_, e in enumerate(rx.process(chunks)):
+            got[s_].extend(e)
+    for s_ in range(len(recs)):
+        assert_events_equal(got[s_], want[s_], f"stream {s_} alternating kernels")
+        o = Oracle(oracle_cfg_from(b))
+        o.process_s16(recs[s_])
+        assert_events_equal(want[s_], o.events(), f"stream {s_} generic kernel vs oracle")
+
+
 def test_other_sample_rates_generic_kernel():
     """44.1 kHz (84 taps, DC length 32) and 48 kHz (92 taps, DC length 35: the DC blocker is no longer exact in f32 and
     must be evaluated sequentially in the reference's order) — SURVEY.md §8f N4."""
