@@ -17,8 +17,9 @@
 #include "same_params.h"
 
 extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps, const SameTaps2* taps2, int force_generic,
-                                      const int16_t* d_samples, const unsigned long long* d_offsets,
-                                      const uint32_t* d_lengths, cudaStream_t stream);
+                                      uint32_t lanes_per_warp, const int16_t* d_samples,
+                                      const unsigned long long* d_offsets, const uint32_t* d_lengths,
+                                      cudaStream_t stream);
 extern "C" cudaError_t same_launch_init(const SameParams* p, const uint32_t* d_ids, uint32_t n, int after_reset,
                                         cudaStream_t stream);
 
@@ -76,6 +77,8 @@ struct same_engine {
   SameTaps taps;
   SameTaps2 taps2;
   int force_generic = 0;
+  uint32_t lanes_per_warp = 32;   // streams per warp in the fast kernel (lane-sparse warps for small batches)
+  int sm_count = 148;
   same_derived derived;
   cudaStream_t compute = nullptr, copy = nullptr;
   uint32_t* d_state = nullptr;
@@ -221,7 +224,7 @@ int submit_common(same_engine* e, const int16_t* host_samples, const int16_t* de
   CK(e, cudaEventRecord(b.copied, e->copy));
   CK(e, cudaStreamWaitEvent(e->compute, b.copied, 0));
   CK(e, cudaEventRecord(e->t_k0, e->compute));
-  CK(e, same_launch_rx(&e->p, &e->taps, &e->taps2, e->force_generic, d_src, b.d_off, b.d_len, e->compute));
+  CK(e, same_launch_rx(&e->p, &e->taps, &e->taps2, e->force_generic, e->lanes_per_warp, d_src, b.d_off, b.d_len, e->compute));
   CK(e, cudaEventRecord(e->t_k1, e->compute));
   CK(e, cudaEventRecord(b.consumed, e->compute));
   b.used = true;
@@ -331,6 +334,20 @@ int same_engine_create(const same_config* cfg_in, int device, uint32_t n_streams
   }
   p.f_one = 1.0f; p.f_negzero = -0.0f;
   if (const char* fg = getenv("SAME_FORCE_GENERIC")) e->force_generic = atoi(fg);
+  {
+    // Lane-sparse warps: aim for ~8 warps per SM (2 per scheduler) before filling all 32 lanes of a warp.
+    int sms = 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
+    e->sm_count = sms;
+    const uint32_t target_warps = (uint32_t)sms * 8u;
+    uint32_t lanes = 1;
+    while (lanes < 32u && (n_streams + lanes - 1u) / lanes > target_warps) lanes <<= 1;
+    e->lanes_per_warp = lanes;
+    if (const char* lw = getenv("SAME_LANES_PER_WARP")) {
+      uint32_t v = (uint32_t)atoi(lw);
+      if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) e->lanes_per_warp = v;
+    }
+  }
   p.spt = sps / 2.0f;                                                         // symsync.rs:146
   {
     float dev = sps * rclampf(cfg.timing_max_deviation, 0.0f, 0.5f);          // symsync.rs:147
@@ -642,6 +659,12 @@ int same_engine_set_option(same_engine* e, const char* key, int value) {
   int rc = same_engine_sync(e);
   if (rc) return rc;
   if (strcmp(key, "force_generic") == 0) { e->force_generic = value; return SAME_OK; }
+  if (strcmp(key, "lanes_per_warp") == 0) {
+    if (!(value == 1 || value == 2 || value == 4 || value == 8 || value == 16 || value == 32))
+      return fail(e, SAME_ERR_INVALID_ARG, "lanes_per_warp must be a power of two in 1..32");
+    e->lanes_per_warp = (uint32_t)value;
+    return SAME_OK;
+  }
   return fail(e, SAME_ERR_INVALID_ARG, std::string("unknown option ") + key);
 }
 

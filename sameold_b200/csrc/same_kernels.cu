@@ -159,16 +159,26 @@ __global__ void __launch_bounds__(32) same_rx_generic_kernel(const __grid_consta
 // ----------------------------------------------------------------------------------------------------------------
 // Fast kernel: ntaps == 42, dc_len == 16 (22050 Hz).
 //
-// Shared memory per warp: d ring [64][32] f32 (DC-blocked samples waiting for the AGC) + y ring [128][32] f32 (AGC
-// output; slot j and its mirror j+64 hold the same sample so that the 42 newest samples are always readable at
-// descending addresses without a wrap).  Sample j of this chunk lives at slot j & 63 in both rings.
+// Shared memory per warp (static, so every access is [register + constant]): d ring [64][32] f32 (DC-blocked samples
+// waiting for the AGC) + y ring [128][32] f32 (AGC output; slot j and its mirror j+64 hold the same sample so that the
+// 42 newest samples are always readable at descending addresses without a wrap) + the 42 taps as float4.
+// Sample j of this chunk lives at slot j & 63 in both rings; [slot][lane] layout: bank == lane, conflict-free for any
+// per-lane slot.
+//
+// `lanes` (1,2,4,...,32) = streams per warp.  Small batches use lane-sparse warps: the per-stream chain is latency
+// bound, so spreading few streams over more warps costs nothing and removes most of the divergence (equalizer bytes,
+// refill alignment, trip-count spread) from each warp.
 // ----------------------------------------------------------------------------------------------------------------
 #define FAST_NTAPS 42
 #define FAST_DCL 16
 #define FAST_CHUNK 16     // samples produced per refill step (== DC length: the S1 history recycles in place)
 #define FAST_RING 64
 
-__device__ __forceinline__ int s16_lo(uint32_t w) { return (int)(short)(w & 0xffffu); }
+__device__ __forceinline__ int s16_lo(uint32_t w) {   // sign-extended low half in one PRMT
+  int r;
+  asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(r) : "r"(w));
+  return r;
+}
 __device__ __forceinline__ int s16_hi(uint32_t w) { return ((int)w) >> 16; }
 __device__ __forceinline__ int s16_at(const uint32_t* w, int i) { return (i & 1) ? s16_hi(w[i >> 1]) : s16_lo(w[i >> 1]); }
 
@@ -176,15 +186,15 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
                                                           const __grid_constant__ SameTaps2 taps,
                                                           const int16_t* __restrict__ samples,
                                                           const unsigned long long* __restrict__ offsets,
-                                                          const uint32_t* __restrict__ lengths) {
-  extern __shared__ float smem[];
-  float* dring = smem;                    // [64][32]
-  float* yring = smem + FAST_RING * 32;   // [128][32]
+                                                          const uint32_t* __restrict__ lengths, const uint32_t lanes) {
+  __shared__ float dring[FAST_RING * 32];
+  __shared__ float yring[2 * FAST_RING * 32];
+  __shared__ float4 tapsm[FAST_NTAPS];
 
   const SameLayout& L = p.layout;
   const int lane = threadIdx.x;
-  const uint32_t s = blockIdx.x * 32u + lane;
-  const bool valid = s < p.n_streams;
+  const uint32_t s = blockIdx.x * lanes + lane;
+  const bool valid = (uint32_t)lane < lanes && s < p.n_streams;
   const uint32_t sidx = valid ? s : 0u;
   uint32_t* st = p.state32 + sidx;
   StreamBlob* blob = p.blobs + sidx;
@@ -210,13 +220,16 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
   }
 #pragma unroll
   for (int i = 0; i < FAST_DCL; ++i) s1h[i] = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_fb + i)) * 16.0f);
-  // demod window -> y ring slots of samples -42..-1 (and mirrors)
+  // demod window -> y ring slots of samples -42..-1 (and mirrors); d ring starts finite (stale slots are read, never used)
+  for (int i = 0; i < FAST_RING; ++i) dring[i * 32 + lane] = 0.0f;
   for (int i = 0; i < FAST_NTAPS; ++i) {
     const float v = __uint_as_float(LANE_ST(st, L, L.win + i));
     const int slot = (i - FAST_NTAPS) & (FAST_RING - 1);
     yring[slot * 32 + lane] = v;
     yring[(slot + FAST_RING) * 32 + lane] = v;
   }
+  for (int i = lane; i < FAST_NTAPS; i += 32)
+    tapsm[i] = make_float4(taps.mark[i].x, taps.mark[i].y, taps.space[i].x, taps.space[i].y);
   __syncwarp();
 
   const float bw = p.agc_bw, gmin = p.agc_min, gmax = p.agc_max;
@@ -227,6 +240,15 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
   bool dc_windows_stored = false;
   int cfire = fire_clock(a.until, a.clock);
 
+  // software prefetch of the next full 16-sample chunk (two 16-byte loads): issued one refill ahead so that the
+  // global-load latency overlaps a whole round of the sequential work
+  int4 nx0 = make_int4(0, 0, 0, 0), nx1 = make_int4(0, 0, 0, 0);
+  bool pf_ok = src != nullptr && src_aligned && len >= (uint32_t)FAST_CHUNK;
+  if (pf_ok) {
+    const int4* q = reinterpret_cast<const int4*>(src);
+    nx0 = __ldg(q); nx1 = __ldg(q + 1);
+  }
+
   while (__any_sync(0xffffffffu, pos < len)) {
     // ---------------- refill: raw s16 -> exact DC-blocked f32 into the d ring (A0, A1) ----------------
     // One uniform decision per warp keeps the lanes' refills aligned (a lane-private decision would make nearly every
@@ -234,74 +256,109 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
     while (__any_sync(0xffffffffu, (rp - pos) < 24u && rp < len)) {
       const bool take = (rp < len) && (rp - pos) <= (uint32_t)(FAST_RING - FAST_CHUNK);
       const uint32_t nnew = take ? min((uint32_t)FAST_CHUNK, len - rp) : 0u;
-      uint32_t cur[FAST_CHUNK / 2];
+      if (nnew == FAST_CHUNK) {
+        // ---- full chunk: everything static, no per-sample predicates ----
+        uint32_t cur[FAST_CHUNK / 2];
+        if (pf_ok) {
+          cur[0] = nx0.x; cur[1] = nx0.y; cur[2] = nx0.z; cur[3] = nx0.w;
+          cur[4] = nx1.x; cur[5] = nx1.y; cur[6] = nx1.z; cur[7] = nx1.w;
+        } else {
 #pragma unroll
-      for (int i = 0; i < FAST_CHUNK / 2; ++i) cur[i] = 0u;
-      if (nnew == FAST_CHUNK && src_aligned) {
-        if (src) {
-          const int4* q = reinterpret_cast<const int4*>(src + rp);
-          const int4 v0 = __ldg(q), v1 = __ldg(q + 1);
-          cur[0] = v0.x; cur[1] = v0.y; cur[2] = v0.z; cur[3] = v0.w;
-          cur[4] = v1.x; cur[5] = v1.y; cur[6] = v1.z; cur[7] = v1.w;
+          for (int i = 0; i < FAST_CHUNK / 2; ++i) {
+            const uint32_t lo = src ? (uint32_t)(uint16_t)src[rp + 2 * i] : 0u;
+            const uint32_t hi = src ? (uint32_t)(uint16_t)src[rp + 2 * i + 1] : 0u;
+            cur[i] = lo | (hi << 16);
+          }
         }
-      } else if (nnew && src) {  // tail of the chunk or unaligned stream start: scalar loads
+        // prefetch the chunk after this one
+        pf_ok = src != nullptr && src_aligned && (len - rp) >= 2u * FAST_CHUNK;
+        if (pf_ok) {
+          const int4* q = reinterpret_cast<const int4*>(src + rp + FAST_CHUNK);
+          nx0 = __ldg(q); nx1 = __ldg(q + 1);
+        }
+        float* dst = dring + (rp & (FAST_RING - 1)) * 32 + lane;  // rp % 16 == 0: the chunk never wraps
 #pragma unroll
         for (int i = 0; i < FAST_CHUNK; ++i) {
-          const uint32_t v = (i < (int)nnew) ? (uint32_t)(uint16_t)src[rp + i] : 0u;
+          const int x = s16_at(cur, i);
+          const int x16 = s16_at(rawh, i);
+          const int x15 = (i < FAST_CHUNK - 1) ? s16_at(rawh, i + 1) : s16_at(cur, 0);
+          S1 += x - x16;                    // ff: moving_sum += input - aged          dcblock.rs:106
+          S2 += S1 - s1h[i];                // fb: moving_sum += ma0 - aged (x16)      dcblock.rs:106
+          s1h[i] = S1;
+          const int D = (x15 << 8) - S2;    // 256 * (sig - ma1)                       dcblock.rs:48
+          dst[i * 32] = (float)D * 0.00390625f;
+        }
+#pragma unroll
+        for (int i = 0; i < FAST_CHUNK / 2; ++i) rawh[i] = cur[i];
+        rp += FAST_CHUNK;
+      } else if (nnew) {
+        // ---- final partial chunk of this submit (rp reaches len): scalar loads, per-sample predicates ----
+        uint32_t cur[FAST_CHUNK / 2];
+#pragma unroll
+        for (int i = 0; i < FAST_CHUNK / 2; ++i) cur[i] = 0u;
+#pragma unroll
+        for (int i = 0; i < FAST_CHUNK; ++i) {
+          const uint32_t v = (src && i < (int)nnew) ? (uint32_t)(uint16_t)src[rp + i] : 0u;
           cur[i >> 1] |= (i & 1) ? (v << 16) : v;
         }
-      }
-      if (nnew) {
-        float* dst = dring + (rp & (FAST_RING - 1)) * 32 + lane;  // rp % 16 == 0: the chunk never wraps
+        float* dst = dring + (rp & (FAST_RING - 1)) * 32 + lane;
 #pragma unroll
         for (int i = 0; i < FAST_CHUNK; ++i) {
           if (i < (int)nnew) {
             const int x = s16_at(cur, i);
             const int x16 = s16_at(rawh, i);
             const int x15 = (i < FAST_CHUNK - 1) ? s16_at(rawh, i + 1) : s16_at(cur, 0);
-            S1 += x - x16;                    // ff: moving_sum += input - aged          dcblock.rs:106
-            S2 += S1 - s1h[i];                // fb: moving_sum += ma0 - aged (x16)      dcblock.rs:106
+            S1 += x - x16;
+            S2 += S1 - s1h[i];
             s1h[i] = S1;
-            const int D = (x15 << 8) - S2;    // 256 * (sig - ma1)                       dcblock.rs:48
+            const int D = (x15 << 8) - S2;
             dst[i * 32] = (float)D * 0.00390625f;
           }
         }
-        if (nnew == FAST_CHUNK) {
+        // The DC windows are final now.  Store them to the state words right here, rotated so that index 0 is the
+        // oldest sample again (static register indices, run-time addresses — no dynamically indexed register arrays).
 #pragma unroll
-          for (int i = 0; i < FAST_CHUNK / 2; ++i) rawh[i] = cur[i];
-        } else {
-          // Final partial chunk of this submit (rp reaches len): the DC windows are final now.  Store them to the
-          // state words right here, rotated so that index 0 is the oldest sample again (static register indices,
-          // run-time addresses — no dynamically indexed register arrays).
-#pragma unroll
-          for (int i = 0; i < FAST_DCL; ++i) {
-            const bool is_old = i >= (int)nnew;
-            const uint32_t dsti = is_old ? (uint32_t)i - nnew : (uint32_t)(FAST_DCL + i) - nnew;
-            const int xv = is_old ? s16_at(rawh, i) : s16_at(cur, i);
-            LANE_ST(st, L, L.dc_ff + dsti) = __float_as_uint((float)xv);
-            LANE_ST(st, L, L.dc_fb + dsti) = __float_as_uint((float)s1h[i] * 0.0625f);
-          }
-          dc_windows_stored = true;
+        for (int i = 0; i < FAST_DCL; ++i) {
+          const bool is_old = i >= (int)nnew;
+          const uint32_t dsti = is_old ? (uint32_t)i - nnew : (uint32_t)(FAST_DCL + i) - nnew;
+          const int xv = is_old ? s16_at(rawh, i) : s16_at(cur, i);
+          LANE_ST(st, L, L.dc_ff + dsti) = __float_as_uint((float)xv);
+          LANE_ST(st, L, L.dc_fb + dsti) = __float_as_uint((float)s1h[i] * 0.0625f);
         }
+        dc_windows_stored = true;
         rp += nnew;
       }
       __syncwarp();
     }
 
     // ---------------- segment: AGC over this lane's samples up to its next TED instant (A2, A3) ----------------
+    // Branch-free: every lane runs the warp's longest trip count; samples beyond a lane's own segment use bandwidth 0
+    // (g + t*0 == g exactly; the stale d they read is finite) and store nothing.  The d loads of a group of four are
+    // issued together so that their latency is paid once per group, not once per sample.
     int nseg = 0;
     if (pos < len) nseg = min(cfire - a.clock, (int)(rp - pos));
     const int maxseg = __reduce_max_sync(0xffffffffu, nseg);
     const float bw_eff = (a.flags & FLAG_AGC_LOCKED) ? 0.0f : bw;   // (!locked as f32) * (1-|y|) * bw   agc.rs:74
     float g = a.g;
-    for (int k = 0; k < maxseg; ++k) {
-      if (k < nseg) {
-        const int slot = (int)((pos + k) & (FAST_RING - 1));
-        const float d = dring[slot * 32 + lane];
-        const float y = FMUL(d, g);                                           // agc.rs:73
-        g = fminf(fmaxf(FADD(g, FMUL(FSUB(1.0f, fabsf(y)), bw_eff)), gmin), gmax);  // agc.rs:74-75
-        yring[slot * 32 + lane] = y;                                          // demod.rs:177-179
-        yring[(slot + FAST_RING) * 32 + lane] = y;
+    const uint32_t lane_off = (uint32_t)lane;
+    for (int k0 = 0; k0 < maxseg; k0 += 4) {
+      float dv[4];
+      uint32_t so[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        so[j] = ((pos + (uint32_t)(k0 + j)) & (FAST_RING - 1)) * 32u + lane_off;
+        dv[j] = dring[so[j]];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool act = (k0 + j) < nseg;
+        const float bwk = act ? bw_eff : 0.0f;
+        const float y = FMUL(dv[j], g);                                               // agc.rs:73
+        g = fminf(fmaxf(FADD(g, FMUL(FSUB(1.0f, fabsf(y)), bwk)), gmin), gmax);       // agc.rs:74-75
+        if (act) {
+          yring[so[j]] = y;                                                           // demod.rs:177-179
+          yring[so[j] + FAST_RING * 32] = y;
+        }
       }
     }
     a.g = g;
@@ -323,9 +380,10 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
 #pragma unroll
       for (int i = 0; i < FAST_NTAPS; ++i) {
         const float v = yp[-i * 32];
+        const float4 t = tapsm[i];
         const float2 vv = make_float2(v, v);
-        am = __ffma2_rn(am, one2, __ffma2_rn(vv, taps.mark[i], negz2));
-        as = __ffma2_rn(as, one2, __ffma2_rn(vv, taps.space[i], negz2));
+        am = __ffma2_rn(am, one2, __ffma2_rn(vv, make_float2(t.x, t.y), negz2));
+        as = __ffma2_rn(as, one2, __ffma2_rn(vv, make_float2(t.z, t.w), negz2));
       }
       soft = rclamp(FSUB(hypot_fixed(am.x, am.y), hypot_fixed(as.x, as.y)), -1.0f, 1.0f);  // demod.rs:163
     }
@@ -387,12 +445,14 @@ __global__ void same_init_kernel(const __grid_constant__ SameParams p, const uin
 // Launchers (called from same_engine.cu)
 // ----------------------------------------------------------------------------------------------------------------
 extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps, const SameTaps2* taps2, int force_generic,
-                                      const int16_t* d_samples, const unsigned long long* d_offsets,
-                                      const uint32_t* d_lengths, cudaStream_t stream) {
+                                      uint32_t lanes_per_warp, const int16_t* d_samples,
+                                      const unsigned long long* d_offsets, const uint32_t* d_lengths,
+                                      cudaStream_t stream) {
   const uint32_t blocks = (p->n_streams + 31u) / 32u;
   if (!force_generic && p->ntaps == FAST_NTAPS && p->dc_len == FAST_DCL) {
-    const size_t smem = (size_t)(FAST_RING + 2 * FAST_RING) * 32 * sizeof(float);
-    same_dev::same_rx_fast_kernel<<<blocks, 32, smem, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths);
+    const uint32_t lanes = lanes_per_warp ? lanes_per_warp : 32u;
+    const uint32_t fblocks = (p->n_streams + lanes - 1u) / lanes;
+    same_dev::same_rx_fast_kernel<<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes);
   } else if (p->ntaps <= 64 && p->dc_len <= 16) {
     const size_t smem = (size_t)(64 + 2 * 16) * 32 * sizeof(float);
     same_dev::same_rx_generic_kernel<64, 16><<<blocks, 32, smem, stream>>>(*p, *taps, d_samples, d_offsets, d_lengths);

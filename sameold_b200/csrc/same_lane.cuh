@@ -119,7 +119,7 @@ __device__ __forceinline__ void lane_load(Lane& a, const SameParams& p, const ui
   a.tr.tr_state = (a.flags >> FLAG_TR_SHIFT) & 3u;
   a.tr.next_deadline = ((unsigned long long)LANE_ST(st, L, F_TRNEXT_HI) << 32) | LANE_ST(st, L, F_TRNEXT_LO);
   a.tr.eom_at = ((unsigned long long)LANE_ST(st, L, F_EOM_HI) << 32) | LANE_ST(st, L, F_EOM_LO);
-  a.ev.p = &p; a.ev.stream = s; a.ev.seq = LANE_ST(st, L, F_SEQ);
+  a.ev.stream = s; a.ev.seq = LANE_ST(st, L, F_SEQ);
   a.trace_n = LANE_ST(st, L, F_TRACE_N);
 }
 
@@ -359,8 +359,12 @@ __device__ __forceinline__ void symbol_step(Lane& a, const SameParams& p, uint32
         a.train_sa = p.sq_sync_word; a.train_cnt = 0;
       }
       uint32_t byte;
-      if (p.eq_nff == 6u && p.eq_nfb == 4u) byte = eq_byte<6, 4, true>(p, s, S, a.flags, a.train_sa, a.train_cnt);
-      else byte = eq_byte<SAME_MAX_EQ, SAME_MAX_EQ, false>(p, s, S, a.flags, a.train_sa, a.train_cnt);
+      {  // by-reference arguments go through short-lived temporaries so that the lane state stays in registers
+        uint32_t fl = a.flags, tsa = a.train_sa, tcn = a.train_cnt;
+        if (p.eq_nff == 6u && p.eq_nfb == 4u) byte = eq_byte<6, 4, true>(p, s, S, fl, tsa, tcn);
+        else byte = eq_byte<SAME_MAX_EQ, SAME_MAX_EQ, false>(p, s, S, fl, tsa, tcn);
+        a.flags = fl; a.train_sa = tsa; a.train_cnt = tcn;
+      }
       ls = framer_input(p, blob, a.fr, byte, adjusted, burst_len);             // receiver.rs:457-459
       if (ls == 2u) a.flags |= FLAG_SQ_LOCK;                                   // receiver.rs:461-465
       else if (ls == 0u || ls == 3u) do_end = true;                            // receiver.rs:466-469
@@ -378,15 +382,16 @@ __device__ __forceinline__ void symbol_step(Lane& a, const SameParams& p, uint32
   if (ls != a.link_last || ls == 3u) {
     a.link_last = ls;
     if (ls == 3u)
-      emit_event(a.ev, SAME_EV_LINK_BURST, 0, n, a.symcount, blob->burst, burst_len, min(burst_len, SAME_BURST_CAP), 0, 0,
+      emit_event(p, a.ev, SAME_EV_LINK_BURST, 0, n, a.symcount, blob->burst, burst_len, min(burst_len, SAME_BURST_CAP), 0, 0,
                  burst_len > SAME_BURST_CAP ? SAME_EV_FLAG_TRUNCATED : 0u);
     else
-      emit_event(a.ev, ls, 0, n, a.symcount, nullptr, 0, 0, 0, 0, 0);
+      emit_event(p, a.ev, ls, 0, n, a.symcount, nullptr, 0, 0, 0, 0, 0);
   }
 
   // transport  receiver.rs:291-333
-  if (ls == 3u || ls == 0u) {
-    Transport& tr = a.tr;
+  if (ls == 3u || (ls == 0u && ((a.tr.have_eom && n > a.tr.eom_at) || a.symcount >= a.tr.next_deadline ||
+                                (a.tr.hist_n ? 1u : 0u) != a.tr.tr_state))) {
+    Transport tr = a.tr;   // copy: the assembler functions are noinline and take it by reference
     uint32_t tk; MsgResult mr; mr.kind = 0; mr.err = 0; mr.len = 0; mr.parity = 0; mr.voting = 0; mr.offset = 0;
     if (ls == 3u) {
       tk = assembler_assemble(p, blob, tr, burst_len, a.symcount, mr);
@@ -403,15 +408,16 @@ __device__ __forceinline__ void symbol_step(Lane& a, const SameParams& p, uint32
       // a Message state always differs from the previous transport state (an idle poll separates messages)
       tr.tr_state = 2;
       if (mr.kind == 0u)
-        emit_event(a.ev, SAME_EV_TR_MSG_SOM, 0, n, a.symcount, blob->pending_text, mr.len, mr.len, mr.parity, mr.voting, 0);
+        emit_event(p, a.ev, SAME_EV_TR_MSG_SOM, 0, n, a.symcount, blob->pending_text, mr.len, mr.len, mr.parity, mr.voting, 0);
       else if (mr.kind == 1u)
-        emit_event(a.ev, SAME_EV_TR_MSG_EOM, 0, n, a.symcount, (const uint8_t*)"NNNN", 4, 4, 0, 0, 0);
+        emit_event(p, a.ev, SAME_EV_TR_MSG_EOM, 0, n, a.symcount, (const uint8_t*)"NNNN", 4, 4, 0, 0, 0);
       else
-        emit_event(a.ev, SAME_EV_TR_MSG_ERR, mr.err, n, a.symcount, nullptr, 0, 0, 0, 0, 0);
+        emit_event(p, a.ev, SAME_EV_TR_MSG_ERR, mr.err, n, a.symcount, nullptr, 0, 0, 0, 0, 0);
     } else if (tk != tr.tr_state) {
       tr.tr_state = tk;
-      emit_event(a.ev, tk == 0u ? SAME_EV_TR_IDLE : SAME_EV_TR_ASSEMBLING, 0, n, a.symcount, nullptr, 0, 0, 0, 0, 0);
+      emit_event(p, a.ev, tk == 0u ? SAME_EV_TR_IDLE : SAME_EV_TR_ASSEMBLING, 0, n, a.symcount, nullptr, 0, 0, 0, 0, 0);
     }
+    a.tr = tr;
   }
 }
 

@@ -17,15 +17,16 @@ namespace same_dev {
 // Event arena
 // ----------------------------------------------------------------------------------------------------------------
 struct EvCtx {
-  const SameParams* p;
   uint32_t stream;
   uint32_t seq;   // per-stream sequence (state)
 };
 
-__device__ __noinline__ void emit_event(EvCtx& c, uint32_t kind, uint32_t err, unsigned long long n,
-                                        unsigned long long symcount, const uint8_t* data, uint32_t data_len,
-                                        uint32_t copy_len, uint32_t parity, uint32_t voting, uint32_t flags) {
-  const SameParams& p = *c.p;
+// Everything is passed by value: a by-reference argument to a noinline function would force the caller's lane state
+// out of registers into local memory for the whole kernel.
+__device__ __noinline__ void emit_event_impl(const SameParams& p, uint32_t stream, uint32_t seq, uint32_t kind,
+                                             uint32_t err, unsigned long long n, unsigned long long symcount,
+                                             const uint8_t* data, uint32_t data_len, uint32_t copy_len, uint32_t parity,
+                                             uint32_t voting, uint32_t flags) {
   unsigned int idx = atomicAdd(&p.counters[0], 1u);
   uint32_t off = 0;
   if (copy_len) {
@@ -35,11 +36,18 @@ __device__ __noinline__ void emit_event(EvCtx& c, uint32_t kind, uint32_t err, u
   }
   if (idx < p.events_cap) {
     same_event e;
-    e.stream = c.stream; e.seq = c.seq; e.input_sample_counter = n; e.symbol_count = symcount;
+    e.stream = stream; e.seq = seq; e.input_sample_counter = n; e.symbol_count = symcount;
     e.kind = kind; e.err = err; e.data_offset = off; e.data_len = data_len;
     e.parity_errors = (uint16_t)parity; e.voting_bytes = (uint16_t)voting; e.flags = flags;
     p.events[idx] = e;
   }
+}
+
+__device__ __forceinline__ void emit_event(const SameParams& p, EvCtx& c, uint32_t kind, uint32_t err,
+                                           unsigned long long n, unsigned long long symcount, const uint8_t* data,
+                                           uint32_t data_len, uint32_t copy_len, uint32_t parity, uint32_t voting,
+                                           uint32_t flags) {
+  emit_event_impl(p, c.stream, c.seq, kind, err, n, symcount, data, data_len, copy_len, parity, voting, flags);
   c.seq += 1;
 }
 

@@ -252,6 +252,29 @@ def test_fast_and_generic_kernels_agree():
         assert_events_equal(want[s_], o.events(), f"stream {s_} generic kernel vs oracle")
 
 
+def test_lane_sparse_warps_give_identical_results():
+    """Small batches run with fewer streams per warp (latency-bound regime); the mapping must not change results."""
+    _torch()
+    ns = 70
+    buf, plans, n, stride = _device_corpus(ns, 8.0, first=500)
+    offsets = np.arange(ns, dtype=np.uint64) * np.uint64(stride)
+    lengths = np.array([n - 13 * s_ for s_ in range(ns)], np.uint32)
+    b = sb.SameReceiverBuilder.samedec(22050)
+    want = None
+    for lanes in (32, 8, 4, 1):
+        rx = b.build_batch(ns)
+        rx.set_option("lanes_per_warp", lanes)
+        rx.submit_device(buf.data_ptr(), ns * stride, offsets, lengths)
+        rx.sync()
+        got = rx.drain_by_stream()
+        if want is None:
+            want = got
+            assert sum(len(g) for g in got) > 50
+        else:
+            for s_ in range(ns):
+                assert_events_equal(got[s_], want[s_], f"lanes={lanes} stream {s_}")
+
+
 def test_other_sample_rates_generic_kernel():
     """44.1 kHz (84 taps, DC length 32) and 48 kHz (92 taps, DC length 35: the DC blocker is no longer exact in f32 and
     must be evaluated sequentially in the reference's order) — SURVEY.md §8f N4."""
