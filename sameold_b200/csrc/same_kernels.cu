@@ -174,6 +174,21 @@ __global__ void __launch_bounds__(32) same_rx_generic_kernel(const __grid_consta
 #define FAST_CHUNK 16     // samples produced per refill step (== DC length: the S1 history recycles in place)
 #define FAST_RING 64
 
+// Explicit shared-memory accesses on 32-bit shared addresses (keeps ptxas from re-deriving the shared window base
+// around every predicated store).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_f32_mirrored(uint32_t addr, float v) {  // y ring slot j and its mirror j + 64
+  asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.f32 [%0+8192], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ int s16_lo(uint32_t w) {   // sign-extended low half in one PRMT
   int r;
   asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(r) : "r"(w));
@@ -234,6 +249,7 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
 
   const float bw = p.agc_bw, gmin = p.agc_min, gmax = p.agc_max;
   const float2 one2 = make_float2(p.f_one, p.f_one), negz2 = make_float2(p.f_negzero, p.f_negzero);
+  const uint32_t d_base = smem_u32(dring), y_base = smem_u32(yring);
 
   uint32_t pos = 0;   // samples consumed by the AGC/TED side
   uint32_t rp = 0;    // samples produced into the d ring (multiple of 16 except after the final partial chunk)
@@ -332,33 +348,41 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
     }
 
     // ---------------- segment: AGC over this lane's samples up to its next TED instant (A2, A3) ----------------
-    // Branch-free: every lane runs the warp's longest trip count; samples beyond a lane's own segment use bandwidth 0
-    // (g + t*0 == g exactly; the stale d they read is finite) and store nothing.  The d loads of a group of four are
-    // issued together so that their latency is paid once per group, not once per sample.
+    // Every lane runs the warp's longest trip count.  The first `nmin` samples (warp minimum) need no predicate at all;
+    // in the short tail, samples beyond a lane's own segment use bandwidth 0 (g + t*0 == g exactly; the stale d they
+    // read is finite) and store nothing.  The d loads of a group are issued together so that their latency is paid
+    // once per group, not once per sample.  Ring addresses are explicit 32-bit shared addresses: byte offset
+    // o = ((pos + k) & 63) * 128 + lane * 4 relative to each ring.
     int nseg = 0;
     if (pos < len) nseg = min(cfire - a.clock, (int)(rp - pos));
     const int maxseg = __reduce_max_sync(0xffffffffu, nseg);
+    const int nmin = __reduce_min_sync(0xffffffffu, nseg);
     const float bw_eff = (a.flags & FLAG_AGC_LOCKED) ? 0.0f : bw;   // (!locked as f32) * (1-|y|) * bw   agc.rs:74
     float g = a.g;
-    const uint32_t lane_off = (uint32_t)lane;
-    for (int k0 = 0; k0 < maxseg; k0 += 4) {
-      float dv[4];
-      uint32_t so[4];
+    uint32_t o = ((pos << 7) & 0x1f80u) | ((uint32_t)lane << 2);
+    int k = 0;
+    for (; k + 4 <= nmin; k += 4) {
+      float dv[4]; uint32_t oo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { oo[j] = o; dv[j] = lds_f32(d_base + o); o = (o + 128u) & 0x1fffu; }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        so[j] = ((pos + (uint32_t)(k0 + j)) & (FAST_RING - 1)) * 32u + lane_off;
-        dv[j] = dring[so[j]];
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool act = (k0 + j) < nseg;
-        const float bwk = act ? bw_eff : 0.0f;
         const float y = FMUL(dv[j], g);                                               // agc.rs:73
-        g = fminf(fmaxf(FADD(g, FMUL(FSUB(1.0f, fabsf(y)), bwk)), gmin), gmax);       // agc.rs:74-75
-        if (act) {
-          yring[so[j]] = y;                                                           // demod.rs:177-179
-          yring[so[j] + FAST_RING * 32] = y;
-        }
+        g = fminf(fmaxf(FADD(g, FMUL(FSUB(1.0f, fabsf(y)), bw_eff)), gmin), gmax);    // agc.rs:74-75
+        sts_f32_mirrored(y_base + oo[j], y);                                          // demod.rs:177-179
+      }
+    }
+    for (; k < maxseg; k += 2) {
+      float dv[2]; uint32_t oo[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { oo[j] = o; dv[j] = lds_f32(d_base + o); o = (o + 128u) & 0x1fffu; }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const bool act = (k + j) < nseg;
+        const float bwk = act ? bw_eff : 0.0f;
+        const float y = FMUL(dv[j], g);
+        g = fminf(fmaxf(FADD(g, FMUL(FSUB(1.0f, fabsf(y)), bwk)), gmin), gmax);
+        if (act) sts_f32_mirrored(y_base + oo[j], y);
       }
     }
     a.g = g;
