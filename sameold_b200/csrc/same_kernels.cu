@@ -255,6 +255,12 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
   uint32_t rp = 0;    // samples produced into the d ring (multiple of 16 except after the final partial chunk)
   bool dc_windows_stored = false;
   int cfire = fire_clock(a.until, a.clock);
+  // Byte-phase alignment: a lane whose squelch hands out a byte parks (consumes nothing) until the next round whose
+  // index is a multiple of 16, where all parked lanes run the equalizer/framer together.  Bytes are 16 TED instants
+  // apart, so after its first wait a lane's bytes keep falling on those rounds: the warp pays for the byte path once
+  // per 16 rounds instead of once per in-burst lane.
+  uint32_t pend = 0;       // SYM_BYTE_READY | SYM_ADJUSTED while parked
+  uint32_t round_ctr = 0;
 
   // software prefetch of the next full 16-sample chunk (two 16-byte loads): issued one refill ahead so that the
   // global-load latency overlaps a whole round of the sequential work
@@ -265,11 +271,13 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
     nx0 = __ldg(q); nx1 = __ldg(q + 1);
   }
 
-  while (__any_sync(0xffffffffu, pos < len)) {
+  while (__any_sync(0xffffffffu, pos < len || pend != 0u)) {
+    round_ctr += 1;
+    const bool byte_round = (round_ctr & 15u) == 0u;
     // ---------------- refill: raw s16 -> exact DC-blocked f32 into the d ring (A0, A1) ----------------
     // One uniform decision per warp keeps the lanes' refills aligned (a lane-private decision would make nearly every
     // round pay for a refill executed by a few lanes).
-    while (__any_sync(0xffffffffu, (rp - pos) < 24u && rp < len)) {
+    while (__any_sync(0xffffffffu, (rp - pos) < 24u && rp < len && pend == 0u)) {
       const bool take = (rp < len) && (rp - pos) <= (uint32_t)(FAST_RING - FAST_CHUNK);
       const uint32_t nnew = take ? min((uint32_t)FAST_CHUNK, len - rp) : 0u;
       if (nnew == FAST_CHUNK) {
@@ -354,7 +362,7 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
     // once per group, not once per sample.  Ring addresses are explicit 32-bit shared addresses: byte offset
     // o = ((pos + k) & 63) * 128 + lane * 4 relative to each ring.
     int nseg = 0;
-    if (pos < len) nseg = min(cfire - a.clock, (int)(rp - pos));
+    if (pos < len && pend == 0u) nseg = min(cfire - a.clock, (int)(rp - pos));
     const int maxseg = __reduce_max_sync(0xffffffffu, nseg);
     const int nmin = __reduce_min_sync(0xffffffffu, nseg);
     const float bw_eff = (a.flags & FLAG_AGC_LOCKED) ? 0.0f : bw;   // (!locked as f32) * (1-|y|) * bw   agc.rs:74
@@ -389,7 +397,8 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
     pos += (uint32_t)nseg;
     a.clock += nseg;
     const bool fire = (nseg > 0) && (a.clock == cfire);
-    if (!__any_sync(0xffffffffu, fire)) continue;
+    bool have_sym = false;
+    if (__any_sync(0xffffffffu, fire)) {
 
     // ---------------- TED instant: matched filters (A4) with packed exact f32 ops ----------------
     // fma(v, h, -0) == RN(v*h) and fma(acc, 1, prod) == RN(acc + prod): two separately rounded operations per tap
@@ -411,17 +420,22 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
       }
       soft = rclamp(FSUB(hypot_fixed(am.x, am.y), hypot_fixed(as.x, as.y)), -1.0f, 1.0f);  // demod.rs:163
     }
-    bool have_sym = false;
     if (fire) {
       const float rem = FSUB(a.until, (float)a.clock);  // receiver.rs:352
       a.clock = 0;
       have_sym = ted_step(a, p, soft, rem);
       cfire = fire_clock(a.until, 0);
     }
-    if (!__any_sync(0xffffffffu, have_sym)) continue;
+    }  // any(fire)
 
-    // ---------------- symbol (A6-A9) ----------------
-    if (have_sym) symbol_step(a, p, s, st, blob, a.ted1, a.ted2, a.n0 + pos);
+    // ---------------- symbol: squelch now (A6), byte path (A7-A9) on the aligned rounds ----------------
+    if (have_sym) pend = symbol_squelch(a, p, s, st, blob, a.ted1, a.ted2, a.n0 + pos);
+    if (byte_round && __any_sync(0xffffffffu, pend != 0u)) {
+      if (pend != 0u) {
+        symbol_byte(a, p, s, st, blob, (pend & SYM_ADJUSTED) != 0u, a.n0 + pos);
+        pend = 0u;
+      }
+    }
   }
 
   if (!valid || len == 0u) return;

@@ -307,70 +307,20 @@ __device__ __forceinline__ bool ted_step(Lane& a, const SameParams& p, float sof
 // ----------------------------------------------------------------------------------------------------------------
 // A6-A9: one symbol through squelch -> equalizer -> framer -> link/transport events (receiver.rs:407-474, 245-265,
 // 291-333).  `n` = input_sample_counter after the sample that produced the symbol.
+//
+// Split in two so that the expensive byte path can be batched across lanes:
+//   symbol_squelch  always runs at once.  Returns SYM_BYTE_READY (bit 0) | adjusted (bit 1) when the squelch emitted
+//                   a byte (SquelchState::Ready); otherwise it finishes the symbol itself (symbol_finish).
+//   symbol_byte     equalizer + framer for a ready byte, then symbol_finish.  The caller may run it later as long as
+//                   the lane consumes no sample in between (nothing the lane can observe changes meanwhile).
 // ----------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void symbol_step(Lane& a, const SameParams& p, uint32_t s, uint32_t* st, StreamBlob* blob,
-                                            float z, float sy, unsigned long long n) {
-  const SameLayout& L = p.layout;
-  if (p.trace && a.trace_n < p.trace_cap) {
-    same_soft_symbol t; t.input_sample_counter = n; t.zero = z; t.sym = sy;
-    p.trace[(size_t)s * p.trace_cap + a.trace_n] = t;
-    a.trace_n += 1;
-  }
-  // squelch  codesquelch.rs:228-304 (sample history: 64-entry ring kept in place in the state words)
-  LANE_ST(st, L, L.sqh + (a.sq_head & 63u)) = __float_as_uint(z);
-  LANE_ST(st, L, L.sqh + ((a.sq_head + 1u) & 63u)) = __float_as_uint(sy);
-  a.sq_head = (a.sq_head + 2u) & 63u;
-  a.sq_data = (a.sq_data >> 1) | ((sy >= 0.0f) ? 0x80000000u : 0u);            // codesquelch.rs:421-428
-  const uint32_t cerr = __popc(a.sq_data ^ p.sq_sync_word);
-  a.sq_power = FADD(a.sq_power, FMUL(FSUB(FMUL(sy, sy), a.sq_power), p.sq_bw));  // codesquelch.rs:483-488
-  a.sq_power = fmaxf(a.sq_power, 0.0f);
-  a.sq_pflags = (a.sq_pflags >> 1) | ((a.sq_power >= p.sq_close) ? 0x80000000u : 0u);
-  a.symcount += 1;
+#define SYM_BYTE_READY 1u
+#define SYM_ADJUSTED 2u
 
-  uint32_t ls;                 // link state kind returned for this symbol
-  uint32_t burst_len = 0;      // valid when ls == 3
-  bool do_end = false;         // SameReceiver::end()  receiver.rs:479-490
-  if (a.symcount < 32ull) {
-    ls = framer_end(a.fr, burst_len);                                          // NoCarrier: receiver.rs:410-413
-  } else {
-    bool adjusted = false, dropped = false;
-    if (!(a.flags & FLAG_SQ_LOCK) && cerr <= p.sq_max_err && a.sq_power >= p.sq_open) {
-      adjusted = (a.byteclk != 0);                                             // codesquelch.rs:243-267
-      a.byteclk = 0;
-    } else if (a.byteclk >= 0 && !(a.sq_pflags & 1u)) {
-      dropped = true;                                                          // codesquelch.rs:270-277
-    }
-    if (dropped) {
-      a.byteclk = -1; do_end = true;
-      ls = framer_end(a.fr, burst_len);                                        // receiver.rs:414-418
-    } else if (a.byteclk < 0) {
-      ls = framer_end(a.fr, burst_len);                                        // NoCarrier
-    } else if (a.byteclk != 0) {
-      a.byteclk = (a.byteclk + 1) & 7;
-      ls = framer_state(a.fr);                                                 // Reading: receiver.rs:419-422
-    } else {
-      a.byteclk = 1;
-      float S[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j)                                             // oldest 16  codesquelch.rs:288-294
-        S[j] = __uint_as_float(LANE_ST(st, L, L.sqh + ((a.sq_head + j) & 63u)));
-      if (adjusted) {                                                          // receiver.rs:423-438
-        a.flags |= FLAG_AGC_LOCKED | FLAG_BW_LOCKED | FLAG_EQ_TRAINING;
-        a.train_sa = p.sq_sync_word; a.train_cnt = 0;
-      }
-      uint32_t byte;
-      {  // by-reference arguments go through short-lived temporaries so that the lane state stays in registers
-        uint32_t fl = a.flags, tsa = a.train_sa, tcn = a.train_cnt;
-        if (p.eq_nff == 6u && p.eq_nfb == 4u) byte = eq_byte<6, 4, true>(p, s, S, fl, tsa, tcn);
-        else byte = eq_byte<SAME_MAX_EQ, SAME_MAX_EQ, false>(p, s, S, fl, tsa, tcn);
-        a.flags = fl; a.train_sa = tsa; a.train_cnt = tcn;
-      }
-      ls = framer_input(p, blob, a.fr, byte, adjusted, burst_len);             // receiver.rs:457-459
-      if (ls == 2u) a.flags |= FLAG_SQ_LOCK;                                   // receiver.rs:461-465
-      else if (ls == 0u || ls == 3u) do_end = true;                            // receiver.rs:466-469
-    }
-  }
-  if (do_end) {
+// SameReceiver::end() + link event + transport for the link state `ls` of this symbol
+__device__ __forceinline__ void symbol_finish(Lane& a, const SameParams& p, uint32_t s, StreamBlob* blob, uint32_t ls,
+                                              uint32_t burst_len, bool do_end, unsigned long long n) {
+  if (do_end) {                                                                // receiver.rs:479-490
     a.flags &= ~(FLAG_AGC_LOCKED | FLAG_SQ_LOCK | FLAG_BW_LOCKED);
     a.byteclk = -1;
     eq_reset(p, s);
@@ -419,6 +369,88 @@ __device__ __forceinline__ void symbol_step(Lane& a, const SameParams& p, uint32
     }
     a.tr = tr;
   }
+}
+
+__device__ __forceinline__ uint32_t symbol_squelch(Lane& a, const SameParams& p, uint32_t s, uint32_t* st,
+                                                   StreamBlob* blob, float z, float sy, unsigned long long n) {
+  const SameLayout& L = p.layout;
+  if (p.trace && a.trace_n < p.trace_cap) {
+    same_soft_symbol t; t.input_sample_counter = n; t.zero = z; t.sym = sy;
+    p.trace[(size_t)s * p.trace_cap + a.trace_n] = t;
+    a.trace_n += 1;
+  }
+  // squelch  codesquelch.rs:228-304 (sample history: 64-entry ring kept in place in the state words)
+  LANE_ST(st, L, L.sqh + (a.sq_head & 63u)) = __float_as_uint(z);
+  LANE_ST(st, L, L.sqh + ((a.sq_head + 1u) & 63u)) = __float_as_uint(sy);
+  a.sq_head = (a.sq_head + 2u) & 63u;
+  a.sq_data = (a.sq_data >> 1) | ((sy >= 0.0f) ? 0x80000000u : 0u);            // codesquelch.rs:421-428
+  const uint32_t cerr = __popc(a.sq_data ^ p.sq_sync_word);
+  a.sq_power = FADD(a.sq_power, FMUL(FSUB(FMUL(sy, sy), a.sq_power), p.sq_bw));  // codesquelch.rs:483-488
+  a.sq_power = fmaxf(a.sq_power, 0.0f);
+  a.sq_pflags = (a.sq_pflags >> 1) | ((a.sq_power >= p.sq_close) ? 0x80000000u : 0u);
+  a.symcount += 1;
+
+  uint32_t ls;                 // link state kind returned for this symbol
+  uint32_t burst_len = 0;      // valid when ls == 3
+  bool do_end = false;         // SameReceiver::end()  receiver.rs:479-490
+  if (a.symcount < 32ull) {
+    ls = framer_end(a.fr, burst_len);                                          // NoCarrier: receiver.rs:410-413
+  } else {
+    bool adjusted = false, dropped = false;
+    if (!(a.flags & FLAG_SQ_LOCK) && cerr <= p.sq_max_err && a.sq_power >= p.sq_open) {
+      adjusted = (a.byteclk != 0);                                             // codesquelch.rs:243-267
+      a.byteclk = 0;
+    } else if (a.byteclk >= 0 && !(a.sq_pflags & 1u)) {
+      dropped = true;                                                          // codesquelch.rs:270-277
+    }
+    if (dropped) {
+      a.byteclk = -1; do_end = true;
+      ls = framer_end(a.fr, burst_len);                                        // receiver.rs:414-418
+    } else if (a.byteclk < 0) {
+      ls = framer_end(a.fr, burst_len);                                        // NoCarrier
+    } else if (a.byteclk != 0) {
+      a.byteclk = (a.byteclk + 1) & 7;
+      ls = framer_state(a.fr);                                                 // Reading: receiver.rs:419-422
+    } else {
+      a.byteclk = 1;                                                           // SquelchState::Ready(adjusted, ..)
+      return SYM_BYTE_READY | (adjusted ? SYM_ADJUSTED : 0u);
+    }
+  }
+  symbol_finish(a, p, s, blob, ls, burst_len, do_end, n);
+  return 0u;
+}
+
+__device__ __forceinline__ void symbol_byte(Lane& a, const SameParams& p, uint32_t s, uint32_t* st, StreamBlob* blob,
+                                            bool adjusted, unsigned long long n) {
+  const SameLayout& L = p.layout;
+  float S[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j)                                                 // oldest 16  codesquelch.rs:288-294
+    S[j] = __uint_as_float(LANE_ST(st, L, L.sqh + ((a.sq_head + j) & 63u)));
+  if (adjusted) {                                                              // receiver.rs:423-438
+    a.flags |= FLAG_AGC_LOCKED | FLAG_BW_LOCKED | FLAG_EQ_TRAINING;
+    a.train_sa = p.sq_sync_word; a.train_cnt = 0;
+  }
+  uint32_t byte;
+  {  // by-reference arguments go through short-lived temporaries so that the lane state stays in registers
+    uint32_t fl = a.flags, tsa = a.train_sa, tcn = a.train_cnt;
+    if (p.eq_nff == 6u && p.eq_nfb == 4u) byte = eq_byte<6, 4, true>(p, s, S, fl, tsa, tcn);
+    else byte = eq_byte<SAME_MAX_EQ, SAME_MAX_EQ, false>(p, s, S, fl, tsa, tcn);
+    a.flags = fl; a.train_sa = tsa; a.train_cnt = tcn;
+  }
+  uint32_t burst_len = 0;
+  bool do_end = false;
+  const uint32_t ls = framer_input(p, blob, a.fr, byte, adjusted, burst_len);  // receiver.rs:457-459
+  if (ls == 2u) a.flags |= FLAG_SQ_LOCK;                                       // receiver.rs:461-465
+  else if (ls == 0u || ls == 3u) do_end = true;                                // receiver.rs:466-469
+  symbol_finish(a, p, s, blob, ls, burst_len, do_end, n);
+}
+
+// Undeferred form (generic kernel)
+__device__ __forceinline__ void symbol_step(Lane& a, const SameParams& p, uint32_t s, uint32_t* st, StreamBlob* blob,
+                                            float z, float sy, unsigned long long n) {
+  const uint32_t r = symbol_squelch(a, p, s, st, blob, z, sy, n);
+  if (r & SYM_BYTE_READY) symbol_byte(a, p, s, st, blob, (r & SYM_ADJUSTED) != 0u, n);
 }
 
 }  // namespace same_dev
