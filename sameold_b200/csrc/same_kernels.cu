@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(32) same_rx_generic_kernel(const __grid_consta
 // ----------------------------------------------------------------------------------------------------------------
 #define FAST_NTAPS 42
 #define FAST_DCL 16
-#define FAST_CHUNK 16     // samples produced per refill step (== DC length: the S1 history recycles in place)
+#define FAST_CHUNK 32     // samples produced per refill step (2 x DC length: the S1 history recycles in place twice)
 #define FAST_RING 64
 
 // Explicit shared-memory accesses on 32-bit shared addresses (keeps ptxas from re-deriving the shared window base
@@ -262,13 +262,16 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
   uint32_t pend = 0;       // SYM_BYTE_READY | SYM_ADJUSTED while parked
   uint32_t round_ctr = 0;
 
-  // software prefetch of the next full 16-sample chunk (two 16-byte loads): issued one refill ahead so that the
-  // global-load latency overlaps a whole round of the sequential work
-  int4 nx0 = make_int4(0, 0, 0, 0), nx1 = make_int4(0, 0, 0, 0);
+  // software prefetch of the next full 32-sample chunk (four 16-byte loads): issued one refill ahead, and a refill
+  // happens at most once per round, so the global-load latency overlaps a whole round of the sequential work
+  int4 nx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) nx[i] = make_int4(0, 0, 0, 0);
   bool pf_ok = src != nullptr && src_aligned && len >= (uint32_t)FAST_CHUNK;
   if (pf_ok) {
     const int4* q = reinterpret_cast<const int4*>(src);
-    nx0 = __ldg(q); nx1 = __ldg(q + 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) nx[i] = __ldg(q + i);
   }
 
   while (__any_sync(0xffffffffu, pos < len || pend != 0u)) {
@@ -284,8 +287,8 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
         // ---- full chunk: everything static, no per-sample predicates ----
         uint32_t cur[FAST_CHUNK / 2];
         if (pf_ok) {
-          cur[0] = nx0.x; cur[1] = nx0.y; cur[2] = nx0.z; cur[3] = nx0.w;
-          cur[4] = nx1.x; cur[5] = nx1.y; cur[6] = nx1.z; cur[7] = nx1.w;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { cur[4 * i] = nx[i].x; cur[4 * i + 1] = nx[i].y; cur[4 * i + 2] = nx[i].z; cur[4 * i + 3] = nx[i].w; }
         } else {
 #pragma unroll
           for (int i = 0; i < FAST_CHUNK / 2; ++i) {
@@ -298,22 +301,23 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
         pf_ok = src != nullptr && src_aligned && (len - rp) >= 2u * FAST_CHUNK;
         if (pf_ok) {
           const int4* q = reinterpret_cast<const int4*>(src + rp + FAST_CHUNK);
-          nx0 = __ldg(q); nx1 = __ldg(q + 1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) nx[i] = __ldg(q + i);
         }
-        float* dst = dring + (rp & (FAST_RING - 1)) * 32 + lane;  // rp % 16 == 0: the chunk never wraps
+        float* dst = dring + (rp & (FAST_RING - 1)) * 32 + lane;  // rp % 32 == 0: the chunk never wraps
 #pragma unroll
         for (int i = 0; i < FAST_CHUNK; ++i) {
           const int x = s16_at(cur, i);
-          const int x16 = s16_at(rawh, i);
-          const int x15 = (i < FAST_CHUNK - 1) ? s16_at(rawh, i + 1) : s16_at(cur, 0);
+          const int x16 = (i < FAST_DCL) ? s16_at(rawh, i) : s16_at(cur, i - FAST_DCL);
+          const int x15 = (i < FAST_DCL - 1) ? s16_at(rawh, i + 1) : s16_at(cur, i - (FAST_DCL - 1));
           S1 += x - x16;                    // ff: moving_sum += input - aged          dcblock.rs:106
-          S2 += S1 - s1h[i];                // fb: moving_sum += ma0 - aged (x16)      dcblock.rs:106
-          s1h[i] = S1;
+          S2 += S1 - s1h[i & 15];           // fb: moving_sum += ma0 - aged            dcblock.rs:106
+          s1h[i & 15] = S1;
           const int D = (x15 << 8) - S2;    // 256 * (sig - ma1)                       dcblock.rs:48
           dst[i * 32] = (float)D * 0.00390625f;
         }
 #pragma unroll
-        for (int i = 0; i < FAST_CHUNK / 2; ++i) rawh[i] = cur[i];
+        for (int i = 0; i < FAST_DCL / 2; ++i) rawh[i] = cur[FAST_CHUNK / 2 - FAST_DCL / 2 + i];
         rp += FAST_CHUNK;
       } else if (nnew) {
         // ---- final partial chunk of this submit (rp reaches len): scalar loads, per-sample predicates ----
@@ -330,24 +334,28 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
         for (int i = 0; i < FAST_CHUNK; ++i) {
           if (i < (int)nnew) {
             const int x = s16_at(cur, i);
-            const int x16 = s16_at(rawh, i);
-            const int x15 = (i < FAST_CHUNK - 1) ? s16_at(rawh, i + 1) : s16_at(cur, 0);
+            const int x16 = (i < FAST_DCL) ? s16_at(rawh, i) : s16_at(cur, i - FAST_DCL);
+            const int x15 = (i < FAST_DCL - 1) ? s16_at(rawh, i + 1) : s16_at(cur, i - (FAST_DCL - 1));
             S1 += x - x16;
-            S2 += S1 - s1h[i];
-            s1h[i] = S1;
+            S2 += S1 - s1h[i & 15];
+            s1h[i & 15] = S1;
             const int D = (x15 << 8) - S2;
             dst[i * 32] = (float)D * 0.00390625f;
           }
         }
         // The DC windows are final now.  Store them to the state words right here, rotated so that index 0 is the
-        // oldest sample again (static register indices, run-time addresses — no dynamically indexed register arrays).
+        // oldest sample again (static register indices, run-time addresses — no dynamically indexed register arrays):
+        // the last 16 samples are old-history entries i >= nnew and chunk samples nnew-16 <= i < nnew; the S1 of chunk
+        // sample j lives in s1h[j & 15].
 #pragma unroll
         for (int i = 0; i < FAST_DCL; ++i) {
-          const bool is_old = i >= (int)nnew;
-          const uint32_t dsti = is_old ? (uint32_t)i - nnew : (uint32_t)(FAST_DCL + i) - nnew;
-          const int xv = is_old ? s16_at(rawh, i) : s16_at(cur, i);
-          LANE_ST(st, L, L.dc_ff + dsti) = __float_as_uint((float)xv);
-          LANE_ST(st, L, L.dc_fb + dsti) = __float_as_uint((float)s1h[i] * 0.0625f);
+          if (i >= (int)nnew) LANE_ST(st, L, L.dc_ff + ((uint32_t)i - nnew)) = __float_as_uint((float)s16_at(rawh, i));
+          LANE_ST(st, L, L.dc_fb + (((uint32_t)i - nnew) & 15u)) = __float_as_uint((float)s1h[i] * 0.0625f);
+        }
+#pragma unroll
+        for (int i = 0; i < FAST_CHUNK; ++i) {
+          if (i < (int)nnew && i + FAST_DCL >= (int)nnew)
+            LANE_ST(st, L, L.dc_ff + ((uint32_t)(i + FAST_DCL) - nnew)) = __float_as_uint((float)s16_at(cur, i));
         }
         dc_windows_stored = true;
         rp += nnew;
