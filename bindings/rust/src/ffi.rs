@@ -1,0 +1,82 @@
+//! Raw bindings to include/same_engine.h (ABI version 1).  Field order and types match the C header exactly.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct same_config {
+    pub input_rate: u32,
+    pub dc_blocker_len: f32,
+    pub agc_bandwidth: f32,
+    pub agc_gain_min: f32,
+    pub agc_gain_max: f32,
+    pub timing_bw_unlocked: f32,
+    pub timing_bw_locked: f32,
+    pub timing_max_deviation: f32,
+    pub squelch_power_open: f32,
+    pub squelch_power_close: f32,
+    pub squelch_bandwidth: f32,
+    pub preamble_max_errors: u32,
+    pub eq_enabled: u32,
+    pub eq_nff: u32,
+    pub eq_nfb: u32,
+    pub eq_relaxation: f32,
+    pub eq_regularization: f32,
+    pub frame_prefix_max_errors: u32,
+    pub frame_max_invalid_bytes: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct same_event {
+    pub stream: u32,
+    pub seq: u32,
+    pub input_sample_counter: u64,
+    pub symbol_count: u64,
+    pub kind: u32,
+    pub err: u32,
+    pub data_offset: u32,
+    pub data_len: u32,
+    pub parity_errors: u16,
+    pub voting_bytes: u16,
+    pub flags: u32,
+}
+
+pub const SAME_EV_LINK_NOCARRIER: u32 = 0;
+pub const SAME_EV_LINK_SEARCHING: u32 = 1;
+pub const SAME_EV_LINK_READING: u32 = 2;
+pub const SAME_EV_LINK_BURST: u32 = 3;
+pub const SAME_EV_TR_IDLE: u32 = 16;
+pub const SAME_EV_TR_ASSEMBLING: u32 = 17;
+pub const SAME_EV_TR_MSG_SOM: u32 = 18;
+pub const SAME_EV_TR_MSG_EOM: u32 = 19;
+pub const SAME_EV_TR_MSG_ERR: u32 = 20;
+
+#[repr(C)]
+pub struct same_engine {
+    _private: [u8; 0],
+}
+
+extern "C" {
+    pub fn same_abi_version() -> u32;
+    pub fn same_config_default(cfg: *mut same_config, input_rate: u32);
+    pub fn same_config_samedec(cfg: *mut same_config, input_rate: u32);
+    pub fn same_config_sanitize(cfg: *mut same_config);
+    pub fn same_engine_create(cfg: *const same_config, device: c_int, n_streams: u32, out: *mut *mut same_engine) -> c_int;
+    pub fn same_engine_destroy(e: *mut same_engine);
+    pub fn same_last_error() -> *const c_char;
+    pub fn same_engine_last_error(e: *const same_engine) -> *const c_char;
+    pub fn same_engine_num_streams(e: *const same_engine) -> u32;
+    pub fn same_engine_input_rate(e: *const same_engine) -> u32;
+    pub fn same_engine_input_sample_counters(e: *mut same_engine, out: *mut u64) -> c_int;
+    pub fn same_engine_reset(e: *mut same_engine, stream_ids: *const u32, n: u32) -> c_int;
+    pub fn same_engine_submit_s16(e: *mut same_engine, samples: *const i16, total_samples: u64, offsets: *const u64, lengths: *const u32) -> c_int;
+    pub fn same_engine_submit_s16_2d(e: *mut same_engine, samples: *const i16, row_stride: u64, col_start: u64, n_cols: u32) -> c_int;
+    pub fn same_engine_submit_zeros(e: *mut same_engine, lengths: *const u32) -> c_int;
+    pub fn same_engine_sync(e: *mut same_engine) -> c_int;
+    pub fn same_engine_pending(e: *mut same_engine, n_events: *mut usize, n_payload: *mut usize) -> c_int;
+    pub fn same_engine_drain_events(e: *mut same_engine, events: *mut same_event, events_cap: usize, n_events: *mut usize,
+                                    payload: *mut u8, payload_cap: usize, n_payload: *mut usize) -> c_int;
+    pub fn same_host_alloc(bytes: usize) -> *mut c_void;
+    pub fn same_host_free(p: *mut c_void);
+}
