@@ -131,10 +131,15 @@ int alloc_arenas(same_engine* e, size_t max_events, size_t max_payload) {
 
 // Pull the events produced since the last collect from the device arenas into the host pending lists.
 int collect(same_engine* e) {
-  CK(e, cudaMemcpyAsync(e->h_counters, e->d_counters, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, e->compute));
+  CK(e, cudaMemcpyAsync(e->h_counters, e->d_counters, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, e->compute));
   CK(e, cudaStreamSynchronize(e->compute));
   const size_t nev = e->h_counters[0], npay = e->h_counters[1];
   int rc = SAME_OK;
+  if (e->h_counters[2] != 0) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "device watchdog tripped (code %u): producer/consumer hand-off stalled", e->h_counters[2]);
+    rc = fail(e, SAME_ERR_CUDA, buf);
+  }
   if (nev > e->events_cap || npay > e->payload_cap) {
     char buf[256];
     snprintf(buf, sizeof buf, "event arena overflow: %zu events / %zu payload bytes produced, capacity %zu / %zu",
@@ -153,7 +158,7 @@ int collect(same_engine* e) {
     CK(e, cudaStreamSynchronize(e->compute));
     for (size_t i = base_ev; i < base_ev + cev; ++i) e->pend_events[i].data_offset += (uint32_t)base_pay;
   }
-  CK(e, cudaMemsetAsync(e->d_counters, 0, 2 * sizeof(unsigned int), e->compute));
+  CK(e, cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(unsigned int), e->compute));
   return rc;
 }
 
@@ -335,11 +340,14 @@ int same_engine_create(const same_config* cfg_in, int device, uint32_t n_streams
   p.f_one = 1.0f; p.f_negzero = -0.0f;
   if (const char* fg = getenv("SAME_FORCE_GENERIC")) e->force_generic = atoi(fg);
   {
-    // Lane-sparse warps: aim for ~8 warps per SM (2 per scheduler) before filling all 32 lanes of a warp.
+    // Lane-sparse warps: aim for ~4 warps per SM (one per scheduler) before filling all 32 lanes of a warp.  Measured
+    // on B200 (4096 x 60 s): 32/16/8 lanes per warp take 140/137/132 ms, 4 lanes 153 ms, 2 lanes 279 ms
+    // (profiles/README.md): a warp that has a scheduler to itself is latency-bound, so fewer lanes per warp only
+    // remove divergence; sharing a scheduler costs more than it hides.
     int sms = 148;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
     e->sm_count = sms;
-    const uint32_t target_warps = (uint32_t)sms * 8u;
+    const uint32_t target_warps = (uint32_t)sms * 4u;
     uint32_t lanes = 1;
     while (lanes < 32u && (n_streams + lanes - 1u) / lanes > target_warps) lanes <<= 1;
     e->lanes_per_warp = lanes;
@@ -402,9 +410,9 @@ int same_engine_create(const same_config* cfg_in, int device, uint32_t n_streams
   CKC(cudaMalloc(&e->d_state, (size_t)L.n_words * L.n_pad * sizeof(uint32_t)));
   CKC(cudaMalloc(&e->d_blobs, (size_t)n_streams * sizeof(StreamBlob)));
   CKC(cudaMemsetAsync(e->d_blobs, 0, (size_t)n_streams * sizeof(StreamBlob), e->compute));
-  CKC(cudaMalloc(&e->d_counters, 2 * sizeof(unsigned int)));
-  CKC(cudaMemsetAsync(e->d_counters, 0, 2 * sizeof(unsigned int), e->compute));
-  CKC(cudaHostAlloc(&e->h_counters, 2 * sizeof(unsigned int), cudaHostAllocDefault));
+  CKC(cudaMalloc(&e->d_counters, 4 * sizeof(unsigned int)));
+  CKC(cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(unsigned int), e->compute));
+  CKC(cudaHostAlloc(&e->h_counters, 4 * sizeof(unsigned int), cudaHostAllocDefault));
   for (auto& b : e->in) {
     CKC(cudaMalloc(&b.d_off, (size_t)n_streams * sizeof(unsigned long long)));
     CKC(cudaMalloc(&b.d_len, (size_t)n_streams * sizeof(uint32_t)));

@@ -463,6 +463,294 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
     LANE_ST(st, L, L.win + i) = __float_as_uint(yring[((int)(len + i - FAST_NTAPS) & (FAST_RING - 1)) * 32 + lane]);
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// Warp-specialised fast kernel: the same algorithm as same_rx_fast_kernel, split over two warps per 32 streams.
+//
+//   warp 1 (producer)  raw s16 -> exact DC-blocked f32 into the d ring (A0, A1): vector loads with one chunk of
+//                      prefetch, integer recursion in registers.  Runs ahead of the consumer by up to the ring size.
+//   warp 0 (consumer)  AGC, matched filters, timing loop, squelch, byte path, events (A2-A9).
+//
+// The two warps sit on different schedulers of the SM, so the refill (global-load latency + ~11 instructions per
+// sample) leaves the consumer's critical path, and each warp needs about half the registers of the fused kernel, which
+// doubles the number of streams resident per SM.  Hand-off: per-lane counters in shared memory (producer publishes
+// `rp` after a block-level fence, consumer publishes `pos`); the consumer never blocks on a lane that is short of data,
+// it just gives that lane no samples this round.  All polling loops are bounded (device watchdog -> counters[2]).
+// ----------------------------------------------------------------------------------------------------------------
+#define WS_SPIN_LIMIT (1u << 24)
+
+__global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ SameParams p,
+                                                        const __grid_constant__ SameTaps2 taps,
+                                                        const int16_t* __restrict__ samples,
+                                                        const unsigned long long* __restrict__ offsets,
+                                                        const uint32_t* __restrict__ lengths, const uint32_t lanes) {
+  __shared__ float dring[FAST_RING * 32];
+  __shared__ float yring[2 * FAST_RING * 32];
+  __shared__ float4 tapsm[FAST_NTAPS];
+  __shared__ volatile uint32_t sh_rp[32];    // samples produced per lane (written by the producer warp)
+  __shared__ volatile uint32_t sh_pos[32];   // samples consumed per lane (written by the consumer warp)
+
+  const SameLayout& L = p.layout;
+  const int lane = threadIdx.x & 31;
+  const int role = threadIdx.x >> 5;         // 0 consumer, 1 producer
+  const uint32_t s = blockIdx.x * lanes + lane;
+  const bool valid = (uint32_t)lane < lanes && s < p.n_streams;
+  const uint32_t sidx = valid ? s : 0u;
+  uint32_t* st = p.state32 + sidx;
+  StreamBlob* blob = p.blobs + sidx;
+
+  const uint32_t len = valid ? lengths[s] : 0u;
+  if (__syncthreads_and(len == 0u)) return;   // block-uniform
+  const int16_t* src = (samples != nullptr && valid) ? samples + offsets[s] : nullptr;
+
+  // ---- shared set-up (both warps) ----
+  for (int i = role; i < FAST_RING; i += 2) dring[i * 32 + lane] = 0.0f;   // stale slots are read, never used: keep them finite
+  if (role == 0) {
+    for (int i = 0; i < FAST_NTAPS; ++i) {   // demod window -> y ring slots of samples -42..-1 (and mirrors)
+      const float v = __uint_as_float(LANE_ST(st, L, L.win + i));
+      const int slot = (i - FAST_NTAPS) & (FAST_RING - 1);
+      yring[slot * 32 + lane] = v;
+      yring[(slot + FAST_RING) * 32 + lane] = v;
+    }
+    sh_pos[lane] = 0u;
+  } else {
+    for (int i = lane; i < FAST_NTAPS; i += 32)
+      tapsm[i] = make_float4(taps.mark[i].x, taps.mark[i].y, taps.space[i].x, taps.space[i].y);
+    sh_rp[lane] = 0u;
+  }
+  __syncthreads();
+
+  if (role == 1) {
+    // =============================================== producer ===============================================
+    const bool src_aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+    uint32_t rawh[FAST_DCL / 2];   // last 16 raw samples, packed pairs, oldest first   (ff window, dcblock.rs:63)
+    int s1h[FAST_DCL];             // S1 = 16 * ma0 for the last 16 samples            (fb window)
+    int S1 = __float2int_rn(__uint_as_float(LANE_ST(st, L, F_DC_FFSUM)));
+    int S2 = __float2int_rn(__uint_as_float(LANE_ST(st, L, F_DC_FBSUM)) * 16.0f);
+#pragma unroll
+    for (int i = 0; i < FAST_DCL / 2; ++i) {
+      int lo = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_ff + 2 * i)));
+      int hi = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_ff + 2 * i + 1)));
+      rawh[i] = ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16);
+    }
+#pragma unroll
+    for (int i = 0; i < FAST_DCL; ++i) s1h[i] = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_fb + i)) * 16.0f);
+
+    uint32_t rp = 0;
+    bool dc_windows_stored = false;
+    int4 nx[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) nx[i] = make_int4(0, 0, 0, 0);
+    bool pf_ok = src != nullptr && src_aligned && len >= (uint32_t)FAST_CHUNK;
+    if (pf_ok) {
+      const int4* q = reinterpret_cast<const int4*>(src);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) nx[i] = __ldg(q + i);
+    }
+    uint32_t spins = 0;
+    while (__any_sync(0xffffffffu, rp < len)) {
+      const uint32_t cpos = sh_pos[lane];
+      // one warp-uniform trigger keeps the lanes' refills aligned; every lane with room for a chunk then takes one
+      if (!__any_sync(0xffffffffu, rp < len && (rp - cpos) < 28u)) {
+        if (++spins > WS_SPIN_LIMIT) { if (lane == 0) atomicOr(&p.counters[2], 1u); break; }
+        __nanosleep(40);
+        continue;
+      }
+      spins = 0;
+      const bool take = (rp < len) && (rp - cpos) <= (uint32_t)(FAST_RING - FAST_CHUNK);
+      const uint32_t nnew = take ? min((uint32_t)FAST_CHUNK, len - rp) : 0u;
+      if (nnew == FAST_CHUNK) {
+        uint32_t cur[FAST_CHUNK / 2];
+        if (pf_ok) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { cur[4 * i] = nx[i].x; cur[4 * i + 1] = nx[i].y; cur[4 * i + 2] = nx[i].z; cur[4 * i + 3] = nx[i].w; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < FAST_CHUNK / 2; ++i) {
+            const uint32_t lo = src ? (uint32_t)(uint16_t)src[rp + 2 * i] : 0u;
+            const uint32_t hi = src ? (uint32_t)(uint16_t)src[rp + 2 * i + 1] : 0u;
+            cur[i] = lo | (hi << 16);
+          }
+        }
+        pf_ok = src != nullptr && src_aligned && (len - rp) >= 2u * FAST_CHUNK;
+        if (pf_ok) {
+          const int4* q = reinterpret_cast<const int4*>(src + rp + FAST_CHUNK);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) nx[i] = __ldg(q + i);
+        }
+        float* dst = dring + (rp & (FAST_RING - 1)) * 32 + lane;  // rp % 32 == 0: the chunk never wraps
+#pragma unroll
+        for (int i = 0; i < FAST_CHUNK; ++i) {
+          const int x = s16_at(cur, i);
+          const int x16 = (i < FAST_DCL) ? s16_at(rawh, i) : s16_at(cur, i - FAST_DCL);
+          const int x15 = (i < FAST_DCL - 1) ? s16_at(rawh, i + 1) : s16_at(cur, i - (FAST_DCL - 1));
+          S1 += x - x16;                    // ff: moving_sum += input - aged          dcblock.rs:106
+          S2 += S1 - s1h[i & 15];           // fb: moving_sum += ma0 - aged            dcblock.rs:106
+          s1h[i & 15] = S1;
+          const int D = (x15 << 8) - S2;    // 256 * (sig - ma1)                       dcblock.rs:48
+          dst[i * 32] = (float)D * 0.00390625f;
+        }
+#pragma unroll
+        for (int i = 0; i < FAST_DCL / 2; ++i) rawh[i] = cur[FAST_CHUNK / 2 - FAST_DCL / 2 + i];
+        rp += FAST_CHUNK;
+      } else if (nnew) {
+        uint32_t cur[FAST_CHUNK / 2];
+#pragma unroll
+        for (int i = 0; i < FAST_CHUNK / 2; ++i) cur[i] = 0u;
+#pragma unroll
+        for (int i = 0; i < FAST_CHUNK; ++i) {
+          const uint32_t v = (src && i < (int)nnew) ? (uint32_t)(uint16_t)src[rp + i] : 0u;
+          cur[i >> 1] |= (i & 1) ? (v << 16) : v;
+        }
+        float* dst = dring + (rp & (FAST_RING - 1)) * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < FAST_CHUNK; ++i) {
+          if (i < (int)nnew) {
+            const int x = s16_at(cur, i);
+            const int x16 = (i < FAST_DCL) ? s16_at(rawh, i) : s16_at(cur, i - FAST_DCL);
+            const int x15 = (i < FAST_DCL - 1) ? s16_at(rawh, i + 1) : s16_at(cur, i - (FAST_DCL - 1));
+            S1 += x - x16;
+            S2 += S1 - s1h[i & 15];
+            s1h[i & 15] = S1;
+            const int D = (x15 << 8) - S2;
+            dst[i * 32] = (float)D * 0.00390625f;
+          }
+        }
+        // final DC windows, rotated so that index 0 is the oldest sample again (see same_rx_fast_kernel)
+#pragma unroll
+        for (int i = 0; i < FAST_DCL; ++i) {
+          if (i >= (int)nnew) LANE_ST(st, L, L.dc_ff + ((uint32_t)i - nnew)) = __float_as_uint((float)s16_at(rawh, i));
+          LANE_ST(st, L, L.dc_fb + (((uint32_t)i - nnew) & 15u)) = __float_as_uint((float)s1h[i] * 0.0625f);
+        }
+#pragma unroll
+        for (int i = 0; i < FAST_CHUNK; ++i) {
+          if (i < (int)nnew && i + FAST_DCL >= (int)nnew)
+            LANE_ST(st, L, L.dc_ff + ((uint32_t)(i + FAST_DCL) - nnew)) = __float_as_uint((float)s16_at(cur, i));
+        }
+        dc_windows_stored = true;
+        rp += nnew;
+      }
+      __threadfence_block();   // the d values must be visible before the new rp is
+      sh_rp[lane] = rp;
+    }
+    if (valid && len != 0u) {
+      LANE_ST(st, L, F_DC_FFSUM) = __float_as_uint((float)S1);
+      LANE_ST(st, L, F_DC_FBSUM) = __float_as_uint((float)S2 * 0.0625f);
+      if (!dc_windows_stored) {
+#pragma unroll
+        for (int i = 0; i < FAST_DCL; ++i) {
+          LANE_ST(st, L, L.dc_ff + i) = __float_as_uint((float)s16_at(rawh, i));
+          LANE_ST(st, L, L.dc_fb + i) = __float_as_uint((float)s1h[i] * 0.0625f);
+        }
+      }
+    }
+    return;
+  }
+
+  // ================================================= consumer =================================================
+  Lane a;
+  lane_load(a, p, st, s);
+  const float bw = p.agc_bw, gmin = p.agc_min, gmax = p.agc_max;
+  const float2 one2 = make_float2(p.f_one, p.f_one), negz2 = make_float2(p.f_negzero, p.f_negzero);
+  const uint32_t d_base = smem_u32(dring), y_base = smem_u32(yring);
+
+  uint32_t pos = 0;
+  int cfire = fire_clock(a.until, a.clock);
+  uint32_t pend = 0;       // SYM_BYTE_READY | SYM_ADJUSTED while parked (byte-phase alignment, see same_rx_fast_kernel)
+  uint32_t round_ctr = 0;
+  uint32_t spins = 0;
+
+  while (__any_sync(0xffffffffu, pos < len || pend != 0u)) {
+    // ---------------- segment: AGC over this lane's samples up to its next TED instant (A2, A3) ----------------
+    const uint32_t rp = sh_rp[lane];
+    __threadfence_block();   // read rp before the d values it covers
+    int nseg = 0;
+    if (pos < len && pend == 0u) nseg = min(cfire - a.clock, (int)(rp - pos));
+    const int maxseg = __reduce_max_sync(0xffffffffu, nseg);
+    if (maxseg == 0 && !__any_sync(0xffffffffu, pend != 0u)) {
+      // every lane is waiting for the producer: nothing to do this round
+      if (++spins > WS_SPIN_LIMIT) { if (lane == 0) atomicOr(&p.counters[2], 2u); break; }
+      __nanosleep(20);
+      continue;
+    }
+    spins = 0;
+    round_ctr += 1;
+    const bool byte_round = (round_ctr & 15u) == 0u;
+    const int nmin = __reduce_min_sync(0xffffffffu, nseg);
+    const float bw_eff = (a.flags & FLAG_AGC_LOCKED) ? 0.0f : bw;   // (!locked as f32) * (1-|y|) * bw   agc.rs:74
+    float g = a.g;
+    uint32_t o = ((pos << 7) & 0x1f80u) | ((uint32_t)lane << 2);
+    int k = 0;
+    for (; k + 4 <= nmin; k += 4) {
+      float dv[4]; uint32_t oo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { oo[j] = o; dv[j] = lds_f32(d_base + o); o = (o + 128u) & 0x1fffu; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float y = FMUL(dv[j], g);                                               // agc.rs:73
+        g = fminf(fmaxf(FADD(g, FMUL(FSUB(1.0f, fabsf(y)), bw_eff)), gmin), gmax);    // agc.rs:74-75
+        sts_f32_mirrored(y_base + oo[j], y);                                          // demod.rs:177-179
+      }
+    }
+    for (; k < maxseg; k += 2) {
+      float dv[2]; uint32_t oo[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { oo[j] = o; dv[j] = lds_f32(d_base + o); o = (o + 128u) & 0x1fffu; }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const bool act = (k + j) < nseg;
+        const float bwk = act ? bw_eff : 0.0f;
+        const float y = FMUL(dv[j], g);
+        g = fminf(fmaxf(FADD(g, FMUL(FSUB(1.0f, fabsf(y)), bwk)), gmin), gmax);
+        if (act) sts_f32_mirrored(y_base + oo[j], y);
+      }
+    }
+    a.g = g;
+    pos += (uint32_t)nseg;
+    a.clock += nseg;
+    sh_pos[lane] = pos;      // lets the producer reuse the ring slots behind pos
+    const bool fire = (nseg > 0) && (a.clock == cfire);
+    bool have_sym = false;
+    if (__any_sync(0xffffffffu, fire)) {
+      // ---------------- TED instant: matched filters (A4) with packed exact f32 ops (see same_rx_fast_kernel) ----------------
+      float soft;
+      {
+        int nslot = (int)((pos - 1u) & (FAST_RING - 1));
+        if (nslot < FAST_NTAPS - 1) nslot += FAST_RING;
+        const float* yp = yring + nslot * 32 + lane;
+        float2 am = make_float2(0.0f, 0.0f), as = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int i = 0; i < FAST_NTAPS; ++i) {
+          const float v = yp[-i * 32];
+          const float4 t = tapsm[i];
+          const float2 vv = make_float2(v, v);
+          am = __ffma2_rn(am, one2, __ffma2_rn(vv, make_float2(t.x, t.y), negz2));
+          as = __ffma2_rn(as, one2, __ffma2_rn(vv, make_float2(t.z, t.w), negz2));
+        }
+        soft = rclamp(FSUB(hypot_fixed(am.x, am.y), hypot_fixed(as.x, as.y)), -1.0f, 1.0f);  // demod.rs:163
+      }
+      if (fire) {
+        const float rem = FSUB(a.until, (float)a.clock);  // receiver.rs:352
+        a.clock = 0;
+        have_sym = ted_step(a, p, soft, rem);
+        cfire = fire_clock(a.until, 0);
+      }
+    }
+    // ---------------- symbol: squelch now (A6), byte path (A7-A9) on the aligned rounds ----------------
+    if (have_sym) pend = symbol_squelch(a, p, s, st, blob, a.ted1, a.ted2, a.n0 + pos);
+    if (byte_round && __any_sync(0xffffffffu, pend != 0u)) {
+      if (pend != 0u) {
+        symbol_byte(a, p, s, st, blob, (pend & SYM_ADJUSTED) != 0u, a.n0 + pos);
+        pend = 0u;
+      }
+    }
+  }
+
+  if (!valid || len == 0u) return;
+  lane_store(a, p, st, a.n0 + pos);
+  for (int i = 0; i < FAST_NTAPS; ++i)
+    LANE_ST(st, L, L.win + i) = __float_as_uint(yring[((int)(pos + i - FAST_NTAPS) & (FAST_RING - 1)) * 32 + lane]);
+}
+
 // Constructor state (receiver.rs:502-560) or SameReceiver::reset (receiver.rs:182-198) for the selected streams.
 // `ids` == nullptr: all streams.  `after_reset`: AGC gain 1.0 (agc.rs:61) instead of min(1, min_gain) (agc.rs:55).
 __global__ void same_init_kernel(const __grid_constant__ SameParams p, const uint32_t* __restrict__ ids, uint32_t n,
@@ -495,10 +783,14 @@ extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps,
                                       const unsigned long long* d_offsets, const uint32_t* d_lengths,
                                       cudaStream_t stream) {
   const uint32_t blocks = (p->n_streams + 31u) / 32u;
-  if (!force_generic && p->ntaps == FAST_NTAPS && p->dc_len == FAST_DCL) {
+  // force_generic: 0 = auto (warp-specialised fast kernel), 1 = generic kernel, 2 = single-warp fast kernel
+  if (force_generic != 1 && p->ntaps == FAST_NTAPS && p->dc_len == FAST_DCL) {
     const uint32_t lanes = lanes_per_warp ? lanes_per_warp : 32u;
     const uint32_t fblocks = (p->n_streams + lanes - 1u) / lanes;
-    same_dev::same_rx_fast_kernel<<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes);
+    if (force_generic == 2)
+      same_dev::same_rx_fast_kernel<<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes);
+    else
+      same_dev::same_rx_ws_kernel<<<fblocks, 64, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes);
   } else if (p->ntaps <= 64 && p->dc_len <= 16) {
     const size_t smem = (size_t)(64 + 2 * 16) * 32 * sizeof(float);
     same_dev::same_rx_generic_kernel<64, 16><<<blocks, 32, smem, stream>>>(*p, *taps, d_samples, d_offsets, d_lengths);

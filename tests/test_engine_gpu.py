@@ -221,9 +221,10 @@ def test_device_and_host_submit_agree_and_ragged_lengths():
 
 
 def test_fast_and_generic_kernels_agree():
-    """The 22050 Hz fast kernel (integer DC blocker, packed FFMA2 matched filter, 16-byte loads) and the rate-generic
-    kernel (literal f32 recursion) must give identical events AND identical resident state: chunks alternate between
-    the two kernels mid-stream, with ragged, odd and unaligned chunk lengths."""
+    """The 22050 Hz fast kernels (integer DC blocker, packed FFMA2 matched filter, 16-byte loads; warp-specialised
+    producer/consumer and single-warp forms) and the rate-generic kernel (literal f32 recursion) must give identical
+    events AND identical resident state: chunks alternate between the three kernels mid-stream, with ragged, odd and
+    unaligned chunk lengths."""
     _torch()
     recs = [load_golden_recording(n) for n in NAMES] + [synth.render_numpy(synth.plan_stream(5, seconds=20.0), 20 * 22050)]
     b = sb.SameReceiverBuilder.samedec(22050)
@@ -236,7 +237,7 @@ def test_fast_and_generic_kernels_agree():
     got = [[] for _ in recs]
     k = 0
     while any(p < len(r) for p, r in zip(pos, recs)):
-        rx.set_option("force_generic", k % 2)
+        rx.set_option("force_generic", k % 3)   # 0 warp-specialised fast kernel, 1 generic, 2 single-warp fast kernel
         k += 1
         chunks = []
         for s_ in range(len(recs)):
