@@ -473,10 +473,16 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
 // The two warps sit on different schedulers of the SM, so the refill (global-load latency + ~11 instructions per
 // sample) leaves the consumer's critical path, and each warp needs about half the registers of the fused kernel, which
 // doubles the number of streams resident per SM.  Hand-off: per-lane counters in shared memory (producer publishes
-// `rp` after a block-level fence, consumer publishes `pos`); the consumer never blocks on a lane that is short of data,
-// it just gives that lane no samples this round.  All polling loops are bounded (device watchdog -> counters[2]).
+// `rp`, consumer publishes `pos`) and two named barriers used in strict alternation — no polling, no sleeping:
+//     consumer round:  bar.sync B_DATA  -> segment (reads d) -> publish pos -> bar.arrive B_POS -> filters/TED/symbol
+//     producer round:  bar.sync B_POS   -> refill lanes that have room      -> publish rp  -> bar.arrive B_DATA
+// so the refill for round r+1 overlaps the matched-filter half of round r, and after every refill each lane holds at
+// least one full segment (>= 32 samples) of data.
 // ----------------------------------------------------------------------------------------------------------------
-#define WS_SPIN_LIMIT (1u << 24)
+#define WS_BAR_DATA 1
+#define WS_BAR_POS 2
+__device__ __forceinline__ void ws_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void ws_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
 __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ SameParams p,
                                                         const __grid_constant__ SameTaps2 taps,
@@ -488,6 +494,7 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
   __shared__ float4 tapsm[FAST_NTAPS];
   __shared__ volatile uint32_t sh_rp[32];    // samples produced per lane (written by the producer warp)
   __shared__ volatile uint32_t sh_pos[32];   // samples consumed per lane (written by the consumer warp)
+  __shared__ volatile uint32_t sh_done;      // consumer -> producer: no more rounds
 
   const SameLayout& L = p.layout;
   const int lane = threadIdx.x & 31;
@@ -512,6 +519,7 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
       yring[(slot + FAST_RING) * 32 + lane] = v;
     }
     sh_pos[lane] = 0u;
+    if (lane == 0) sh_done = 0u;
   } else {
     for (int i = lane; i < FAST_NTAPS; i += 32)
       tapsm[i] = make_float4(taps.mark[i].x, taps.mark[i].y, taps.space[i].x, taps.space[i].y);
@@ -546,16 +554,15 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
 #pragma unroll
       for (int i = 0; i < 4; ++i) nx[i] = __ldg(q + i);
     }
-    uint32_t spins = 0;
-    while (__any_sync(0xffffffffu, rp < len)) {
-      const uint32_t cpos = sh_pos[lane];
-      // one warp-uniform trigger keeps the lanes' refills aligned; every lane with room for a chunk then takes one
-      if (!__any_sync(0xffffffffu, rp < len && (rp - cpos) < 28u)) {
-        if (++spins > WS_SPIN_LIMIT) { if (lane == 0) atomicOr(&p.counters[2], 1u); break; }
-        __nanosleep(40);
-        continue;
+    bool first = true;
+    while (true) {
+      if (!first) {
+        ws_bar_sync(WS_BAR_POS);           // the consumer finished a segment and published pos
+        if (sh_done) break;
       }
-      spins = 0;
+      first = false;
+      const uint32_t cpos = sh_pos[lane];
+      // every lane with room for a whole chunk takes one: afterwards it holds >= 32 samples, more than any segment
       const bool take = (rp < len) && (rp - cpos) <= (uint32_t)(FAST_RING - FAST_CHUNK);
       const uint32_t nnew = take ? min((uint32_t)FAST_CHUNK, len - rp) : 0u;
       if (nnew == FAST_CHUNK) {
@@ -629,8 +636,9 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
         dc_windows_stored = true;
         rp += nnew;
       }
-      __threadfence_block();   // the d values must be visible before the new rp is
       sh_rp[lane] = rp;
+      __threadfence_block();             // d values and rp visible before the consumer is released
+      ws_bar_arrive(WS_BAR_DATA);
     }
     if (valid && len != 0u) {
       LANE_ST(st, L, F_DC_FFSUM) = __float_as_uint((float)S1);
@@ -657,22 +665,20 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
   int cfire = fire_clock(a.until, a.clock);
   uint32_t pend = 0;       // SYM_BYTE_READY | SYM_ADJUSTED while parked (byte-phase alignment, see same_rx_fast_kernel)
   uint32_t round_ctr = 0;
-  uint32_t spins = 0;
 
-  while (__any_sync(0xffffffffu, pos < len || pend != 0u)) {
+  while (true) {
+    ws_bar_sync(WS_BAR_DATA);              // the producer's refill for this round is complete and visible
+    if (!__any_sync(0xffffffffu, pos < len || pend != 0u)) {
+      if (lane == 0) sh_done = 1u;
+      __threadfence_block();
+      ws_bar_arrive(WS_BAR_POS);
+      break;
+    }
     // ---------------- segment: AGC over this lane's samples up to its next TED instant (A2, A3) ----------------
     const uint32_t rp = sh_rp[lane];
-    __threadfence_block();   // read rp before the d values it covers
     int nseg = 0;
     if (pos < len && pend == 0u) nseg = min(cfire - a.clock, (int)(rp - pos));
     const int maxseg = __reduce_max_sync(0xffffffffu, nseg);
-    if (maxseg == 0 && !__any_sync(0xffffffffu, pend != 0u)) {
-      // every lane is waiting for the producer: nothing to do this round
-      if (++spins > WS_SPIN_LIMIT) { if (lane == 0) atomicOr(&p.counters[2], 2u); break; }
-      __nanosleep(20);
-      continue;
-    }
-    spins = 0;
     round_ctr += 1;
     const bool byte_round = (round_ctr & 15u) == 0u;
     const int nmin = __reduce_min_sync(0xffffffffu, nseg);
@@ -708,6 +714,8 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
     pos += (uint32_t)nseg;
     a.clock += nseg;
     sh_pos[lane] = pos;      // lets the producer reuse the ring slots behind pos
+    __threadfence_block();
+    ws_bar_arrive(WS_BAR_POS);
     const bool fire = (nseg > 0) && (a.clock == cfire);
     bool have_sym = false;
     if (__any_sync(0xffffffffu, fire)) {
