@@ -79,6 +79,7 @@ struct same_engine {
   int force_generic = 0;
   uint32_t lanes_per_warp = 32;   // streams per warp in the fast kernel (lane-sparse warps for small batches)
   int sm_count = 148;
+  int kernel_auto = 0;            // fast-kernel flavour when force_generic == 0: 0 warp-specialised, 2 single-warp
   same_derived derived;
   cudaStream_t compute = nullptr, copy = nullptr;
   uint32_t* d_state = nullptr;
@@ -229,7 +230,7 @@ int submit_common(same_engine* e, const int16_t* host_samples, const int16_t* de
   CK(e, cudaEventRecord(b.copied, e->copy));
   CK(e, cudaStreamWaitEvent(e->compute, b.copied, 0));
   CK(e, cudaEventRecord(e->t_k0, e->compute));
-  CK(e, same_launch_rx(&e->p, &e->taps, &e->taps2, e->force_generic, e->lanes_per_warp, d_src, b.d_off, b.d_len, e->compute));
+  CK(e, same_launch_rx(&e->p, &e->taps, &e->taps2, e->force_generic ? e->force_generic : e->kernel_auto, e->lanes_per_warp, d_src, b.d_off, b.d_len, e->compute));
   CK(e, cudaEventRecord(e->t_k1, e->compute));
   CK(e, cudaEventRecord(b.consumed, e->compute));
   b.used = true;
@@ -340,21 +341,23 @@ int same_engine_create(const same_config* cfg_in, int device, uint32_t n_streams
   p.f_one = 1.0f; p.f_negzero = -0.0f;
   if (const char* fg = getenv("SAME_FORCE_GENERIC")) e->force_generic = atoi(fg);
   {
-    // Lane-sparse warps: aim for ~4 warps per SM (one per scheduler) before filling all 32 lanes of a warp.  Measured
-    // on B200 (4096 x 60 s): 32/16/8 lanes per warp take 140/137/132 ms, 4 lanes 153 ms, 2 lanes 279 ms
-    // (profiles/README.md): a warp that has a scheduler to itself is latency-bound, so fewer lanes per warp only
-    // remove divergence; sharing a scheduler costs more than it hides.
+    // Kernel / mapping policy for the 22050 Hz class (measured on B200, profiles/README.md):
+    //  * up to 2 blocks per SM: warp-specialised kernel, 32 streams per block.  Each warp has a scheduler to itself,
+    //    the chain is latency-bound, and moving the refill to a second warp shortens every round.
+    //  * larger batches: single-warp fast kernel, 32 streams per warp (issue-bound regime: the fewest instructions win
+    //    and a producer warp per block would only compete for issue slots).
+    // SAME_LANES_PER_WARP / option "lanes_per_warp" spread streams over more, lane-sparse warps (diagnostic).
     int sms = 148;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
     e->sm_count = sms;
-    const uint32_t target_warps = (uint32_t)sms * 4u;
-    uint32_t lanes = 1;
-    while (lanes < 32u && (n_streams + lanes - 1u) / lanes > target_warps) lanes <<= 1;
-    e->lanes_per_warp = lanes;
+    e->lanes_per_warp = 32;
+    const uint32_t blocks32 = (n_streams + 31u) / 32u;
+    e->kernel_auto = (blocks32 <= 2u * (uint32_t)sms) ? 0 : 2;   // 0 = warp-specialised, 2 = single-warp fast
     if (const char* lw = getenv("SAME_LANES_PER_WARP")) {
       uint32_t v = (uint32_t)atoi(lw);
       if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) e->lanes_per_warp = v;
     }
+    if (const char* kv = getenv("SAME_KERNEL")) e->kernel_auto = atoi(kv) == 2 ? 2 : 0;
   }
   p.spt = sps / 2.0f;                                                         // symsync.rs:146
   {
