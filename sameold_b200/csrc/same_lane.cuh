@@ -227,10 +227,11 @@ __device__ __forceinline__ void eq_symbol(const SameParams& p, EqRegs<NFF, NFB>&
   bit = sym_est >= 0.0f;
 }
 
-// EXACT: the tap counts equal the template sizes (compile-time constants -> everything stays in registers)
+// EXACT: the tap counts equal the template sizes (compile-time constants -> everything stays in registers, and the
+// eight symbols are unrolled so that the 16 input samples are read from registers too)
 template <int NFF, int NFB, bool EXACT>
-__device__ __noinline__ uint32_t eq_byte(const SameParams& p, uint32_t s, const float* S, uint32_t& flags,
-                                         uint32_t& train_sa, uint32_t& train_cnt) {
+__device__ __forceinline__ uint32_t eq_byte_impl(const SameParams& p, uint32_t s, const float* S, uint32_t& flags,
+                                                 uint32_t& train_sa, uint32_t& train_cnt) {
   const SameLayout& L = p.layout;
   const int nff = EXACT ? NFF : (int)p.eq_nff, nfb = EXACT ? NFB : (int)p.eq_nfb;
   uint32_t* st = p.state32 + s;
@@ -246,11 +247,20 @@ __device__ __noinline__ uint32_t eq_byte(const SameParams& p, uint32_t s, const 
     q.fbw[i] = __uint_as_float(st[(size_t)(L.eq_fbw + i) * L.n_pad]);
   }
   uint32_t byte = 0;
+  if (EXACT) {
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {  // equalize.rs:173-186, LSb first
+      bool bit;
+      eq_symbol<NFF, NFB>(p, q, nff, nfb, S[2 * b], S[2 * b + 1], flags, train_sa, train_cnt, bit);
+      byte |= (bit ? 1u : 0u) << b;
+    }
+  } else {
 #pragma unroll 1
-  for (int b = 0; b < 8; ++b) {  // equalize.rs:173-186, LSb first
-    bool bit;
-    eq_symbol<NFF, NFB>(p, q, nff, nfb, S[2 * b], S[2 * b + 1], flags, train_sa, train_cnt, bit);
-    byte |= (bit ? 1u : 0u) << b;
+    for (int b = 0; b < 8; ++b) {
+      bool bit;
+      eq_symbol<NFF, NFB>(p, q, nff, nfb, S[2 * b], S[2 * b + 1], flags, train_sa, train_cnt, bit);
+      byte |= (bit ? 1u : 0u) << b;
+    }
   }
 #pragma unroll
   for (int i = 0; i < NFF; ++i) if (i < nff) {
@@ -263,6 +273,12 @@ __device__ __noinline__ uint32_t eq_byte(const SameParams& p, uint32_t s, const 
     st[(size_t)(L.eq_fbw + i) * L.n_pad] = __float_as_uint(q.fbw[i]);
   }
   return byte;
+}
+
+// rate-generic equalizer (any order up to 16/16): out of line, arrays in local memory
+__device__ __noinline__ uint32_t eq_byte_generic(const SameParams& p, uint32_t s, const float* S, uint32_t& flags,
+                                                 uint32_t& train_sa, uint32_t& train_cnt) {
+  return eq_byte_impl<SAME_MAX_EQ, SAME_MAX_EQ, false>(p, s, S, flags, train_sa, train_cnt);
 }
 
 // Equalizer::reset  equalize.rs:191-196 (mode is kept)
@@ -432,10 +448,11 @@ __device__ __forceinline__ void symbol_byte(Lane& a, const SameParams& p, uint32
     a.train_sa = p.sq_sync_word; a.train_cnt = 0;
   }
   uint32_t byte;
-  {  // by-reference arguments go through short-lived temporaries so that the lane state stays in registers
+  if (p.eq_nff == 6u && p.eq_nfb == 4u) {
+    byte = eq_byte_impl<6, 4, true>(p, s, S, a.flags, a.train_sa, a.train_cnt);   // inlined: S and the taps stay in registers
+  } else {  // by-reference arguments go through short-lived temporaries so that the lane state stays in registers
     uint32_t fl = a.flags, tsa = a.train_sa, tcn = a.train_cnt;
-    if (p.eq_nff == 6u && p.eq_nfb == 4u) byte = eq_byte<6, 4, true>(p, s, S, fl, tsa, tcn);
-    else byte = eq_byte<SAME_MAX_EQ, SAME_MAX_EQ, false>(p, s, S, fl, tsa, tcn);
+    byte = eq_byte_generic(p, s, S, fl, tsa, tcn);
     a.flags = fl; a.train_sa = tsa; a.train_cnt = tcn;
   }
   uint32_t burst_len = 0;

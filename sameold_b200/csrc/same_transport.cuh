@@ -21,6 +21,24 @@ struct EvCtx {
   uint32_t seq;   // per-stream sequence (state)
 };
 
+// Word-wise copy of `nbytes` (rounded up to whole words: every byte buffer in StreamBlob and the payload arena is
+// 4-byte aligned and sized in whole words).  Loads of a group are issued before its stores so that their latencies
+// overlap — this code runs on one lane while 31 others wait.
+__device__ __forceinline__ void copy_words(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t nbytes) {
+  const uint32_t nw = (nbytes + 3u) >> 2;
+  uint32_t* __restrict__ d = reinterpret_cast<uint32_t*>(dst);
+  const uint32_t* __restrict__ q = reinterpret_cast<const uint32_t*>(src);
+  uint32_t i = 0;
+  for (; i + 8 <= nw; i += 8) {
+    uint32_t t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = q[i + k];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[i + k] = t[k];
+  }
+  for (; i < nw; ++i) d[i] = q[i];
+}
+
 // Everything is passed by value: a by-reference argument to a noinline function would force the caller's lane state
 // out of registers into local memory for the whole kernel.
 __device__ __noinline__ void emit_event_impl(const SameParams& p, uint32_t stream, uint32_t seq, uint32_t kind,
@@ -30,9 +48,12 @@ __device__ __noinline__ void emit_event_impl(const SameParams& p, uint32_t strea
   unsigned int idx = atomicAdd(&p.counters[0], 1u);
   uint32_t off = 0;
   if (copy_len) {
-    off = atomicAdd(&p.counters[1], (copy_len + 3u) & ~3u);
-    if ((unsigned long long)off + copy_len <= p.payload_cap)
-      for (uint32_t i = 0; i < copy_len; ++i) p.payload[off + i] = data[i];
+    const uint32_t padded = (copy_len + 3u) & ~3u;
+    off = atomicAdd(&p.counters[1], padded);   // offsets stay multiples of 4
+    if ((unsigned long long)off + padded <= p.payload_cap) {
+      if ((reinterpret_cast<uintptr_t>(data) & 3u) == 0) copy_words(p.payload + off, data, copy_len);
+      else for (uint32_t i = 0; i < copy_len; ++i) p.payload[off + i] = data[i];
+    }
   }
   if (idx < p.events_cap) {
     same_event e;
@@ -198,7 +219,7 @@ __device__ __noinline__ void prune_history(StreamBlob* b, Transport& t, unsigned
     if (b->hist[k].deadline <= now) continue;
     if (w != k) {
       b->hist[w].deadline = b->hist[k].deadline; b->hist[w].len = b->hist[k].len;
-      for (uint32_t i = 0; i < b->hist[k].len; ++i) b->hist[w].data[i] = b->hist[k].data[i];
+      copy_words(b->hist[w].data, b->hist[k].data, b->hist[k].len);
     }
     ++w;
   }
@@ -206,36 +227,60 @@ __device__ __noinline__ void prune_history(StreamBlob* b, Transport& t, unsigned
   while (t.hist_n > 2) {  // pop_front
     for (uint32_t k = 0; k + 1 < t.hist_n; ++k) {
       b->hist[k].deadline = b->hist[k + 1].deadline; b->hist[k].len = b->hist[k + 1].len;
-      for (uint32_t i = 0; i < b->hist[k + 1].len; ++i) b->hist[k].data[i] = b->hist[k + 1].data[i];
+      copy_words(b->hist[k].data, b->hist[k + 1].data, b->hist[k + 1].len);
     }
     t.hist_n -= 1;
   }
 }
 
 // combiner.rs:154-203 + 32-80.  Returns false for `None`.  The estimate is left in b->est[0..good_len).
+// The three bursts are read one 32-bit word (4 message bytes) at a time and the estimate / burst-count / bit-error
+// arrays are written one word at a time; the per-byte voting logic itself is the reference's, on register values.
 __device__ __noinline__ bool combine(StreamBlob* b, const Transport& t, MsgResult& res) {
-  uint32_t nb = min(t.hist_n, 3u);
+  const uint32_t nb = min(t.hist_n, 3u);
+  const uint32_t l0 = nb > 0 ? b->hist[0].len : 0u, l1 = nb > 1 ? b->hist[1].len : 0u, l2 = nb > 2 ? b->hist[2].len : 0u;
+  const uint32_t* w0 = reinterpret_cast<const uint32_t*>(b->hist[0].data);
+  const uint32_t* w1 = reinterpret_cast<const uint32_t*>(b->hist[1].data);
+  const uint32_t* w2 = reinterpret_cast<const uint32_t*>(b->hist[2].data);
+  uint32_t* est_w = reinterpret_cast<uint32_t*>(b->est);
+  uint32_t* nb_w = reinterpret_cast<uint32_t*>(b->est_nb);
+  uint32_t* er_w = reinterpret_cast<uint32_t*>(b->est_err);
   uint32_t n = 0;
-  while (n < SAME_MAX_MESSAGE_LENGTH) {
-    uint32_t cur[3]; uint32_t nc = 0;
-    for (uint32_t k = 0; k < nb; ++k)  // every burst iterator advances in lock step (one byte per output byte)
-      if (n < b->hist[k].len) cur[nc++] = b->hist[k].data[n];
-    bool msb = false;
-    for (uint32_t k = 0; k < nc; ++k) { msb = msb || (cur[k] & 0x80u); cur[k] &= 0x7fu; }
-    uint32_t est, be;
-    if (nc == 0) break;
-    if (nc == 1) { est = cur[0]; be = 0; }
-    else if (nc == 2) {  // bit_vote_detect combiner.rs:216-222
-      uint32_t x = cur[0] ^ cur[1];
-      est = x ? 0u : cur[0]; be = __popc(x);
-    } else {             // bit_vote_correct combiner.rs:234-249
-      uint32_t p0 = ~(cur[0] ^ cur[1]) & 0xffu, p1 = ~(cur[1] ^ cur[2]) & 0xffu, p2 = ~(cur[0] ^ cur[2]) & 0xffu;
-      est = (cur[0] & p0) | (cur[2] & p1) | (cur[2] & p2);
-      be = 8u - __popc(p0 & p1 & p2);
+  bool stop = false;
+  for (uint32_t w = 0; w < SAME_MAX_MESSAGE_LENGTH / 4 && !stop; ++w) {
+    const uint32_t base = 4u * w;
+    const uint32_t x0 = base < l0 ? w0[w] : 0u, x1 = base < l1 ? w1[w] : 0u, x2 = base < l2 ? w2[w] : 0u;
+    uint32_t oe = 0, on = 0, orr = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) {
+      if (stop) break;
+      const uint32_t i = base + j;
+      // every burst iterator advances in lock step (one byte per output byte); exhausted bursts drop out
+      const bool h0 = i < l0, h1 = i < l1, h2 = i < l2;
+      const uint32_t nc = (h0 ? 1u : 0u) + (h1 ? 1u : 0u) + (h2 ? 1u : 0u);
+      if (nc == 0) { stop = true; break; }
+      const uint32_t r0 = (x0 >> (8 * j)) & 0xffu, r1 = (x1 >> (8 * j)) & 0xffu, r2 = (x2 >> (8 * j)) & 0xffu;
+      // the (up to three) present bytes in burst order
+      const uint32_t c0 = h0 ? r0 : (h1 ? r1 : r2);
+      const uint32_t c1 = h0 ? (h1 ? r1 : r2) : r2;
+      const uint32_t c2 = r2;
+      const bool msb = ((h0 ? r0 : 0u) | (h1 ? r1 : 0u) | (h2 ? r2 : 0u)) & 0x80u;   // SAME bytes never have the MSb set
+      const uint32_t a0 = c0 & 0x7fu, a1 = c1 & 0x7fu, a2 = c2 & 0x7fu;
+      uint32_t est, be;
+      if (nc == 1) { est = a0; be = 0; }
+      else if (nc == 2) {  // bit_vote_detect combiner.rs:216-222
+        const uint32_t x = a0 ^ a1;
+        est = x ? 0u : a0; be = __popc(x);
+      } else {             // bit_vote_correct combiner.rs:234-249
+        const uint32_t p0 = ~(a0 ^ a1) & 0xffu, p1 = ~(a1 ^ a2) & 0xffu, p2 = ~(a0 ^ a2) & 0xffu;
+        est = (a0 & p0) | (a2 & p1) | (a2 & p2);
+        be = 8u - __popc(p0 & p1 & p2);
+      }
+      if (!is_allowed_byte(est)) { stop = true; break; }
+      oe |= est << (8 * j); on |= nc << (8 * j); orr |= (be + (msb ? 1u : 0u)) << (8 * j);
+      ++n;
     }
-    if (!is_allowed_byte(est)) break;
-    b->est[n] = (uint8_t)est; b->est_nb[n] = (uint8_t)nc; b->est_err[n] = (uint8_t)(be + (msb ? 1u : 0u));
-    ++n;
+    est_w[w] = oe; nb_w[w] = on; er_w[w] = orr;
   }
   if (n == 0) return false;
   uint32_t good = 0;  // truncate_bytes_with_reference(msg, burst_count, 2)  combiner.rs:262-271
@@ -284,7 +329,7 @@ __device__ __noinline__ void pending_accept(const SameParams& p, StreamBlob* b, 
   b->pending_deadline = dl; b->pending_kind = (uint8_t)r.kind; b->pending_err = (uint8_t)r.err;
   b->pending_len = (uint16_t)r.len; b->pending_parity = (uint16_t)r.parity; b->pending_voting = (uint16_t)r.voting;
   b->pending_offset = (uint16_t)r.offset;
-  if (r.kind == 0) for (uint32_t i = 0; i < r.len; ++i) b->pending_text[i] = b->est[i];
+  if (r.kind == 0) copy_words(b->pending_text, b->est, r.len);
   else if (r.kind == 1) { b->pending_text[0] = 'N'; b->pending_text[1] = 'N'; b->pending_text[2] = 'N'; b->pending_text[3] = 'N'; }
 }
 
@@ -302,7 +347,7 @@ __device__ __noinline__ uint32_t assembler_idle(const SameParams& p, StreamBlob*
       t.have_prev = true;
       b->prev_deadline = now + p.history_symbols;
       b->prev_len = (uint16_t)out.len;
-      for (uint32_t i = 0; i < out.len; ++i) b->prev_text[i] = b->pending_text[i];
+      copy_words(b->prev_text, b->pending_text, out.len);
     }
     kind = 2;
   } else kind = t.hist_n ? 1u : 0u;
@@ -319,7 +364,7 @@ __device__ __noinline__ uint32_t assembler_assemble(const SameParams& p, StreamB
   uint32_t n = min(burst_len, (uint32_t)SAME_MAX_MESSAGE_LENGTH);
   BurstSlot& slot = b->hist[t.hist_n];  // hist_n <= 2 after pruning
   slot.deadline = now + p.history_symbols; slot.len = n;
-  for (uint32_t i = 0; i < n; ++i) slot.data[i] = b->burst[i];
+  copy_words(slot.data, b->burst, n);
   t.hist_n += 1;
   MsgResult r;
   if (combine(b, t, r)) {

@@ -42,14 +42,19 @@ int main(int argc, char** argv) {
     const uint32_t want[5] = {SAME_EV_LINK_SEARCHING, SAME_EV_LINK_READING, SAME_EV_LINK_BURST, SAME_EV_TR_ASSEMBLING, SAME_EV_LINK_NOCARRIER};
     for (int i = 0; i < 5; ++i) CHECK(evs[i].kind == want[i]);
     CHECK(evs[2].burst() && std::string(evs[2].data.begin(), evs[2].data.end()).rfind("ZCZC-PEP-NPT-000000+0030-2771820-TEST    -", 0) == 0);
-    // rest of the recording, then flush(): the header comes out of the flush and iter_messages stays empty before
+    // rest of the recording: the header is released 682 symbols after the third burst, still inside the file
     auto msgs = one.iter_messages(std::vector<int16_t>(recs[1].begin() + 30000, recs[1].end()));
-    CHECK(msgs.empty());
-    auto m = one.flush();
-    CHECK(m && m->is_start && m->text == lines[1][0] && m->voting_byte_count == 42 && m->parity_error_count == 0);
+    CHECK(msgs.size() == 1 && msgs[0].is_start && msgs[0].text == lines[1][0] && msgs[0].voting_byte_count == 42 &&
+          msgs[0].parity_error_count == 0);
     CHECK(!one.flush());
     one.reset();
     CHECK(one.input_sample_counter() == 0);
+    // long_message is cut close: iter_messages sees nothing, flush() releases the header and stops there
+    CHECK(one.iter_messages(recs[0]).empty());
+    auto m = one.flush();
+    CHECK(m && m->is_start && m->text == lines[0][0] && m->voting_byte_count == 252 && m->parity_error_count == 0);
+    CHECK(one.input_sample_counter() > recs[0].size() && one.input_sample_counter() < recs[0].size() + 4 * 22050);
+    CHECK(!one.flush());
     std::printf("CPP_OK\n");
     return 0;
   } catch (const same::EngineError& e) {
