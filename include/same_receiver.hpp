@@ -226,7 +226,10 @@ class SameReceiver {
   uint32_t input_rate() const { return b_.input_rate(); }
   uint64_t input_sample_counter() { return b_.input_sample_counters()[0]; }
   void reset() { b_.reset(); }
-  std::vector<SameReceiverEvent> iter_events(const std::vector<int16_t>& samples) { return std::move(b_.process({samples})[0]); }   // receiver.rs:119-130
+  std::vector<SameReceiverEvent> iter_events(const std::vector<int16_t>& samples) {                                               // receiver.rs:119-130
+    auto evs = b_.process({samples});
+    return std::move(evs[0]);
+  }
   std::vector<Message> iter_messages(const std::vector<int16_t>& samples) {                                                        // receiver.rs:155-161
     std::vector<Message> out;
     for (auto& e : iter_events(samples)) if (auto m = e.message_ok()) out.push_back(*m);
@@ -239,7 +242,8 @@ class SameReceiver {
     b_.ck(same_engine_snapshot(b_.e_, &snap));
     const uint64_t start = input_sample_counter();
     std::optional<Message> found; uint64_t at = 0;
-    for (auto& e : b_.process_zeros({nflush})[0]) if (auto m = e.message_ok()) { found = m; at = e.input_sample_counter; break; }
+    auto flushed = b_.process_zeros({nflush});
+    for (auto& e : flushed[0]) if (auto m = e.message_ok()) { found = m; at = e.input_sample_counter; break; }
     if (found) {
       b_.ck(same_engine_restore(b_.e_, snap));
       (void)b_.process_zeros({(uint32_t)(at - start)});

@@ -620,11 +620,25 @@ int same_engine_drain_events(same_engine* e, same_event* events, size_t events_c
   if (n_payload) *n_payload = npay;
   if (nev > events_cap || npay > payload_cap || (nev && !events) || (npay && !payload))
     return fail(e, SAME_ERR_INVALID_ARG, "drain buffers too small");
-  // per-stream order of occurrence, as iter_events yields them (receiver.rs:238-240, 267-269)
-  std::stable_sort(e->pend_events.begin(), e->pend_events.end(), [](const same_event& a, const same_event& b) {
-    return a.stream != b.stream ? a.stream < b.stream : a.seq < b.seq;
-  });
-  if (nev) memcpy(events, e->pend_events.data(), nev * sizeof(same_event));
+  // per-stream order of occurrence, as iter_events yields them (receiver.rs:238-240, 267-269): counting sort by
+  // stream straight into the caller's buffer, then order each stream's few events by sequence number
+  if (nev) {
+    std::vector<uint32_t> start(e->n_streams + 1, 0);
+    for (const same_event& ev : e->pend_events) start[std::min(ev.stream, e->n_streams - 1) + 1] += 1;
+    for (uint32_t i = 0; i < e->n_streams; ++i) start[i + 1] += start[i];
+    std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+    for (const same_event& ev : e->pend_events) events[fill[std::min(ev.stream, e->n_streams - 1)]++] = ev;
+    for (uint32_t i = 0; i < e->n_streams; ++i) {
+      same_event* a = events + start[i];
+      const uint32_t m = start[i + 1] - start[i];
+      for (uint32_t j = 1; j < m; ++j) {   // insertion sort: nearly sorted, a handful of events per stream
+        same_event t = a[j];
+        uint32_t k = j;
+        while (k > 0 && a[k - 1].seq > t.seq) { a[k] = a[k - 1]; --k; }
+        a[k] = t;
+      }
+    }
+  }
   if (npay) memcpy(payload, e->pend_payload.data(), npay);
   e->pend_events.clear(); e->pend_payload.clear();
   return SAME_OK;
