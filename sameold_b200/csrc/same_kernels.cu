@@ -479,6 +479,8 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
 // so the refill for round r+1 overlaps the matched-filter half of round r, and after every refill each lane holds at
 // least one full segment (>= 32 samples) of data.
 // ----------------------------------------------------------------------------------------------------------------
+#define WS_DRING 128       // d ring slots of the warp-specialised kernel
+#define WS_SPEC 16         // look-ahead samples (below the shortest segment of the default timing loop, 19)
 #define WS_BAR_DATA 1
 #define WS_BAR_POS 2
 __device__ __forceinline__ void ws_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
                                                         const int16_t* __restrict__ samples,
                                                         const unsigned long long* __restrict__ offsets,
                                                         const uint32_t* __restrict__ lengths, const uint32_t lanes) {
-  __shared__ float dring[FAST_RING * 32];
+  __shared__ float dring[WS_DRING * 32];   // 128 slots: room for a whole segment of look-ahead (speculative AGC)
   __shared__ float yring[2 * FAST_RING * 32];
   __shared__ float4 tapsm[FAST_NTAPS];
   __shared__ volatile uint32_t sh_rp[32];    // samples produced per lane (written by the producer warp)
@@ -510,7 +512,7 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
   const int16_t* src = (samples != nullptr && valid) ? samples + offsets[s] : nullptr;
 
   // ---- shared set-up (both warps) ----
-  for (int i = role; i < FAST_RING; i += 2) dring[i * 32 + lane] = 0.0f;   // stale slots are read, never used: keep them finite
+  for (int i = role; i < WS_DRING; i += 2) dring[i * 32 + lane] = 0.0f;   // stale slots are read, never used: keep them finite
   if (role == 0) {
     for (int i = 0; i < FAST_NTAPS; ++i) {   // demod window -> y ring slots of samples -42..-1 (and mirrors)
       const float v = __uint_as_float(LANE_ST(st, L, L.win + i));
@@ -563,7 +565,7 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
       first = false;
       const uint32_t cpos = sh_pos[lane];
       // every lane with room for a whole chunk takes one: afterwards it holds >= 32 samples, more than any segment
-      const bool take = (rp < len) && (rp - cpos) <= (uint32_t)(FAST_RING - FAST_CHUNK);
+      const bool take = (rp < len) && (rp - cpos) <= (uint32_t)(WS_DRING - FAST_CHUNK);
       const uint32_t nnew = take ? min((uint32_t)FAST_CHUNK, len - rp) : 0u;
       if (nnew == FAST_CHUNK) {
         uint32_t cur[FAST_CHUNK / 2];
@@ -584,7 +586,7 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 4; ++i) nx[i] = __ldg(q + i);
         }
-        float* dst = dring + (rp & (FAST_RING - 1)) * 32 + lane;  // rp % 32 == 0: the chunk never wraps
+        float* dst = dring + (rp & (WS_DRING - 1)) * 32 + lane;  // rp % 32 == 0: the chunk never wraps
 #pragma unroll
         for (int i = 0; i < FAST_CHUNK; ++i) {
           const int x = s16_at(cur, i);
@@ -608,7 +610,7 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
           const uint32_t v = (src && i < (int)nnew) ? (uint32_t)(uint16_t)src[rp + i] : 0u;
           cur[i >> 1] |= (i & 1) ? (v << 16) : v;
         }
-        float* dst = dring + (rp & (FAST_RING - 1)) * 32 + lane;
+        float* dst = dring + (rp & (WS_DRING - 1)) * 32 + lane;
 #pragma unroll
         for (int i = 0; i < FAST_CHUNK; ++i) {
           if (i < (int)nnew) {
@@ -665,6 +667,12 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
   int cfire = fire_clock(a.until, a.clock);
   uint32_t pend = 0;       // SYM_BYTE_READY | SYM_ADJUSTED while parked (byte-phase alignment, see same_rx_fast_kernel)
   uint32_t round_ctr = 0;
+  // Speculative look-ahead: while the matched filters of round r run (a 42-deep dependent chain that leaves most issue
+  // slots empty), the AGC recurrence of the first WS_SPEC samples of round r+1 is evaluated in the same instruction
+  // stream.  The AGC does not depend on the timing loop, only on the lock flag, so the look-ahead is exact unless the
+  // symbol processing of round r flips that flag (a few times per burst) — then it is thrown away and redone.
+  bool pre_ok = false;     // g_pre / the y ring already hold samples pos .. pos+WS_SPEC-1
+  float g_pre = 0.0f;
 
   while (true) {
     ws_bar_sync(WS_BAR_DATA);              // the producer's refill for this round is complete and visible
@@ -683,13 +691,19 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
     const bool byte_round = (round_ctr & 15u) == 0u;
     const int nmin = __reduce_min_sync(0xffffffffu, nseg);
     const float bw_eff = (a.flags & FLAG_AGC_LOCKED) ? 0.0f : bw;   // (!locked as f32) * (1-|y|) * bw   agc.rs:74
-    float g = a.g;
-    uint32_t o = ((pos << 7) & 0x1f80u) | ((uint32_t)lane << 2);
-    int k = 0;
+    // use the look-ahead only if every lane that works this round has one (uniform start index keeps the loop simple)
+    const bool use_pre = __all_sync(0xffffffffu, nseg == 0 || (pre_ok && nseg >= WS_SPEC));
+    float g = use_pre ? g_pre : a.g;
+    int k = use_pre ? WS_SPEC : 0;
+    uint32_t od = (((pos + (uint32_t)k) << 7) & 0x3f80u) | ((uint32_t)lane << 2);   // d ring: 128 slots
+    uint32_t oy = (((pos + (uint32_t)k) << 7) & 0x1f80u) | ((uint32_t)lane << 2);   // y ring: 64 slots + mirror
     for (; k + 4 <= nmin; k += 4) {
       float dv[4]; uint32_t oo[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { oo[j] = o; dv[j] = lds_f32(d_base + o); o = (o + 128u) & 0x1fffu; }
+      for (int j = 0; j < 4; ++j) {
+        oo[j] = oy; dv[j] = lds_f32(d_base + od);
+        od = (od + 128u) & 0x3fffu; oy = (oy + 128u) & 0x1fffu;
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float y = FMUL(dv[j], g);                                               // agc.rs:73
@@ -700,7 +714,10 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
     for (; k < maxseg; k += 2) {
       float dv[2]; uint32_t oo[2];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) { oo[j] = o; dv[j] = lds_f32(d_base + o); o = (o + 128u) & 0x1fffu; }
+      for (int j = 0; j < 2; ++j) {
+        oo[j] = oy; dv[j] = lds_f32(d_base + od);
+        od = (od + 128u) & 0x3fffu; oy = (oy + 128u) & 0x1fffu;
+      }
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const bool act = (k + j) < nseg;
@@ -710,7 +727,8 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
         if (act) sts_f32_mirrored(y_base + oo[j], y);
       }
     }
-    a.g = g;
+    if (nseg > 0) a.g = g;
+    pre_ok = false;
     pos += (uint32_t)nseg;
     a.clock += nseg;
     sh_pos[lane] = pos;      // lets the producer reuse the ring slots behind pos
@@ -718,7 +736,24 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
     ws_bar_arrive(WS_BAR_POS);
     const bool fire = (nseg > 0) && (a.clock == cfire);
     bool have_sym = false;
+    const uint32_t lock_before = a.flags & FLAG_AGC_LOCKED;
+    bool spec = false;
+    float gs = a.g;
     if (__any_sync(0xffffffffu, fire)) {
+      // ---------------- look-ahead AGC of samples pos .. pos+WS_SPEC-1 (interleaves with the filters below) ----------------
+      spec = fire && (rp - pos) >= (uint32_t)WS_SPEC && (len - pos) >= (uint32_t)WS_SPEC;
+      {
+        uint32_t sd = ((pos << 7) & 0x3f80u) | ((uint32_t)lane << 2);
+        uint32_t sy = ((pos << 7) & 0x1f80u) | ((uint32_t)lane << 2);
+#pragma unroll
+        for (int j = 0; j < WS_SPEC; ++j) {
+          const float d = lds_f32(d_base + sd);
+          const float y = FMUL(d, gs);
+          gs = fminf(fmaxf(FADD(gs, FMUL(FSUB(1.0f, fabsf(y)), bw_eff)), gmin), gmax);
+          if (spec) sts_f32_mirrored(y_base + sy, y);
+          sd = (sd + 128u) & 0x3fffu; sy = (sy + 128u) & 0x1fffu;
+        }
+      }
       // ---------------- TED instant: matched filters (A4) with packed exact f32 ops (see same_rx_fast_kernel) ----------------
       float soft;
       {
@@ -751,6 +786,8 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
         pend = 0u;
       }
     }
+    // the look-ahead stands if this lane is not parked and its AGC lock flag is what the look-ahead assumed
+    if (spec && pend == 0u && (a.flags & FLAG_AGC_LOCKED) == lock_before) { pre_ok = true; g_pre = gs; }
   }
 
   if (!valid || len == 0u) return;
