@@ -740,29 +740,33 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
     bool spec = false;
     float gs = a.g;
     if (__any_sync(0xffffffffu, fire)) {
-      // ---------------- look-ahead AGC of samples pos .. pos+WS_SPEC-1 (interleaves with the filters below) ----------------
+      // ---------------- TED instant: matched filters (A4) with packed exact f32 ops (see same_rx_fast_kernel),
+      //                  with the look-ahead AGC of samples pos .. pos+WS_SPEC-1 woven between the taps ----------------
+      // ptxas keeps shared-memory loads and stores in program order (it cannot prove the ring slots distinct), so the
+      // two independent dependency chains are interleaved here in the source: one AGC step every 2-3 taps.
       spec = fire && (rp - pos) >= (uint32_t)WS_SPEC && (len - pos) >= (uint32_t)WS_SPEC;
+      float soft;
       {
+        float dsp[WS_SPEC];
         uint32_t sd = ((pos << 7) & 0x3f80u) | ((uint32_t)lane << 2);
         uint32_t sy = ((pos << 7) & 0x1f80u) | ((uint32_t)lane << 2);
 #pragma unroll
-        for (int j = 0; j < WS_SPEC; ++j) {
-          const float d = lds_f32(d_base + sd);
-          const float y = FMUL(d, gs);
-          gs = fminf(fmaxf(FADD(gs, FMUL(FSUB(1.0f, fabsf(y)), bw_eff)), gmin), gmax);
-          if (spec) sts_f32_mirrored(y_base + sy, y);
-          sd = (sd + 128u) & 0x3fffu; sy = (sy + 128u) & 0x1fffu;
-        }
-      }
-      // ---------------- TED instant: matched filters (A4) with packed exact f32 ops (see same_rx_fast_kernel) ----------------
-      float soft;
-      {
+        for (int j = 0; j < WS_SPEC; ++j) { dsp[j] = lds_f32(d_base + sd); sd = (sd + 128u) & 0x3fffu; }
         int nslot = (int)((pos - 1u) & (FAST_RING - 1));
         if (nslot < FAST_NTAPS - 1) nslot += FAST_RING;
         const float* yp = yring + nslot * 32 + lane;
         float2 am = make_float2(0.0f, 0.0f), as = make_float2(0.0f, 0.0f);
 #pragma unroll
         for (int i = 0; i < FAST_NTAPS; ++i) {
+#pragma unroll
+          for (int j = 0; j < WS_SPEC; ++j) {
+            if ((j * FAST_NTAPS) / WS_SPEC == i) {   // compile-time schedule: look-ahead sample j rides with tap i
+              const float y = FMUL(dsp[j], gs);
+              gs = fminf(fmaxf(FADD(gs, FMUL(FSUB(1.0f, fabsf(y)), bw_eff)), gmin), gmax);
+              if (spec) sts_f32_mirrored(y_base + sy, y);
+              sy = (sy + 128u) & 0x1fffu;
+            }
+          }
           const float v = yp[-i * 32];
           const float4 t = tapsm[i];
           const float2 vv = make_float2(v, v);
