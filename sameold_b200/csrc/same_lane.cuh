@@ -34,24 +34,27 @@ __device__ __forceinline__ float hypot_fixed(float re, float im) {
   return __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b))));
 }
 
-// receiver.rs:352-353 fires at the first clock value c with  r = until - (c as f32);  r <= 0 || |r| < 0.5
-__device__ __forceinline__ bool fires(float until, int c) {
-  float r = FSUB(until, (float)c);
+// receiver.rs:352-353 fires at the first clock value c with  r = until - (c as f32);  r <= 0 || |r| < 0.5.
+// `cf` is the clock value as an exactly representable float (small integer), so FSUB(until, cf) is the reference's
+// subtraction bit for bit.
+__device__ __forceinline__ bool fires(float until, float cf) {
+  const float r = FSUB(until, cf);
   return r <= 0.0f || fabsf(r) < 0.5f;
 }
 // Smallest c > clock_now that fires.  The predicate is monotone in c, so the closed form floor(until-0.5)+1 is
-// verified against the reference predicate and corrected if a rounding corner case ever disagrees.
+// verified against the reference predicate and corrected if a rounding corner case ever disagrees.  Integer<->float
+// conversions use the 2^23 magic-number form (FMA/ALU pipes) instead of the conversion unit.
 __device__ __forceinline__ int fire_clock(float until, int clock_now) {
-  float t = until - 0.5f;
-  int c = (t < 1.0e6f) ? (int)floorf(t) + 1 : 1000001;
-  if (c < 1) c = 1;
-  if (!fires(until, c)) {
+  float t = fminf(fmaxf(until - 0.5f, 0.0f), 4.0e6f);
+  float cf = FSUB(__fadd_rd(t, 8388608.0f), 8388608.0f) + 1.0f;   // floor(t) + 1 for 0 <= t < 2^23
+  if (!fires(until, cf)) {
     int guard = 0;
-    do { ++c; } while (!fires(until, c) && ++guard < 64);
-  } else if (c > 1 && fires(until, c - 1)) {
+    do { cf += 1.0f; } while (!fires(until, cf) && ++guard < 64);
+  } else if (cf > 1.0f && fires(until, cf - 1.0f)) {
     int guard = 0;
-    do { --c; } while (c > 1 && fires(until, c - 1) && ++guard < 64);
+    do { cf -= 1.0f; } while (cf > 1.0f && fires(until, cf - 1.0f) && ++guard < 64);
   }
+  int c = __float_as_int(cf + 12582912.0f) - 0x4B400000;           // exact for integers |c| < 2^22
   if (c <= clock_now) c = clock_now + 1;
   return c;
 }
@@ -406,32 +409,25 @@ __device__ __forceinline__ uint32_t symbol_squelch(Lane& a, const SameParams& p,
   a.sq_pflags = (a.sq_pflags >> 1) | ((a.sq_power >= p.sq_close) ? 0x80000000u : 0u);
   a.symcount += 1;
 
-  uint32_t ls;                 // link state kind returned for this symbol
-  uint32_t burst_len = 0;      // valid when ls == 3
-  bool do_end = false;         // SameReceiver::end()  receiver.rs:479-490
-  if (a.symcount < 32ull) {
-    ls = framer_end(a.fr, burst_len);                                          // NoCarrier: receiver.rs:410-413
-  } else {
-    bool adjusted = false, dropped = false;
-    if (!(a.flags & FLAG_SQ_LOCK) && cerr <= p.sq_max_err && a.sq_power >= p.sq_open) {
-      adjusted = (a.byteclk != 0);                                             // codesquelch.rs:243-267
-      a.byteclk = 0;
-    } else if (a.byteclk >= 0 && !(a.sq_pflags & 1u)) {
-      dropped = true;                                                          // codesquelch.rs:270-277
-    }
-    if (dropped) {
-      a.byteclk = -1; do_end = true;
-      ls = framer_end(a.fr, burst_len);                                        // receiver.rs:414-418
-    } else if (a.byteclk < 0) {
-      ls = framer_end(a.fr, burst_len);                                        // NoCarrier
-    } else if (a.byteclk != 0) {
-      a.byteclk = (a.byteclk + 1) & 7;
-      ls = framer_state(a.fr);                                                 // Reading: receiver.rs:419-422
-    } else {
-      a.byteclk = 1;                                                           // SquelchState::Ready(adjusted, ..)
-      return SYM_BYTE_READY | (adjusted ? SYM_ADJUSTED : 0u);
-    }
+  // Squelch decision (codesquelch.rs:236-304) as straight-line selects: lanes of a warp are in different squelch
+  // states all the time during bursts, so separate branches per state would all be executed one after the other.
+  const bool full = a.symcount >= 32ull;                                       // sample_history.is_full()
+  const bool acquire = full && !(a.flags & FLAG_SQ_LOCK) && cerr <= p.sq_max_err && a.sq_power >= p.sq_open;
+  const bool adjusted = acquire && a.byteclk != 0;                             // codesquelch.rs:243-267
+  const bool dropped = full && !acquire && a.byteclk >= 0 && !(a.sq_pflags & 1u);   // codesquelch.rs:270-277
+  int bc = acquire ? 0 : a.byteclk;
+  if (dropped) bc = -1;
+  const bool synced = full && bc >= 0;
+  if (synced && bc == 0) {
+    a.byteclk = 1;                                                             // SquelchState::Ready(adjusted, ..)
+    return SYM_BYTE_READY | (adjusted ? SYM_ADJUSTED : 0u);
   }
+  a.byteclk = synced ? ((bc + 1) & 7) : bc;
+  // Reading -> framer.state() (receiver.rs:419-422); NoCarrier / DroppedCarrier -> framer.end() (receiver.rs:410-418)
+  uint32_t burst_len = 0;
+  uint32_t ls = framer_state(a.fr);
+  if (!synced) ls = framer_end(a.fr, burst_len);
+  const bool do_end = dropped;                                                 // SameReceiver::end()  receiver.rs:414-418
   symbol_finish(a, p, s, blob, ls, burst_len, do_end, n);
   return 0u;
 }
