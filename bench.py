@@ -263,8 +263,8 @@ def main():
         barrier()
         e2e_ms = max_over_ranks(e2e_ms)
         e2e = {"value": round(audio_per_step * args.steps * world / (e2e_ms * 1e-3), 1), "unit": UNIT,
-               "h2d_bytes_per_step": int(ns * n_samples * 2 + nchunk * ns * 12),
-               "d2h_bytes_per_step": int(statistics.mean(d2h_bytes)), "ms_per_step": round(e2e_ms / args.steps, 3),
+               "h2d_bytes_per_step": int(ns * n_samples * 2 + nchunk * ns * 12) * world,
+               "d2h_bytes_per_step": int(sum_over_ranks(statistics.mean(d2h_bytes))), "ms_per_step": round(e2e_ms / args.steps, 3),
                "chunks_per_step": nchunk, "api": "same_engine_submit_s16_2d + sync + drain_events (pinned host buffer)"}
 
     # ---- CPU baseline on rank 0 at N=1 ----
