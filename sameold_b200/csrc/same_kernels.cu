@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
 // least one full segment (>= 32 samples) of data.
 // ----------------------------------------------------------------------------------------------------------------
 #define WS_DRING 128       // d ring slots of the warp-specialised kernel
-#define WS_SPEC 16         // look-ahead samples (below the shortest segment of the default timing loop, 19)
+#define WS_SPEC 22         // look-ahead samples: 42 taps + 22 new samples just fit the 64-slot y ring; covers most whole segments
 #define WS_BAR_DATA 1
 #define WS_BAR_POS 2
 __device__ __forceinline__ void ws_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
@@ -494,6 +494,7 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
   __shared__ float dring[WS_DRING * 32];   // 128 slots: room for a whole segment of look-ahead (speculative AGC)
   __shared__ float yring[2 * FAST_RING * 32];
   __shared__ float4 tapsm[FAST_NTAPS];
+  __shared__ float gring[WS_SPEC * 32];      // look-ahead AGC gain after each look-ahead sample
   __shared__ volatile uint32_t sh_rp[32];    // samples produced per lane (written by the producer warp)
   __shared__ volatile uint32_t sh_pos[32];   // samples consumed per lane (written by the consumer warp)
   __shared__ volatile uint32_t sh_done;      // consumer -> producer: no more rounds
@@ -668,11 +669,11 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
   uint32_t pend = 0;       // SYM_BYTE_READY | SYM_ADJUSTED while parked (byte-phase alignment, see same_rx_fast_kernel)
   uint32_t round_ctr = 0;
   // Speculative look-ahead: while the matched filters of round r run (a 42-deep dependent chain that leaves most issue
-  // slots empty), the AGC recurrence of the first WS_SPEC samples of round r+1 is evaluated in the same instruction
-  // stream.  The AGC does not depend on the timing loop, only on the lock flag, so the look-ahead is exact unless the
-  // symbol processing of round r flips that flag (a few times per burst) — then it is thrown away and redone.
-  bool pre_ok = false;     // g_pre / the y ring already hold samples pos .. pos+WS_SPEC-1
-  float g_pre = 0.0f;
+  // slots empty), the AGC recurrence of the next WS_SPEC samples — normally the whole segment of round r+1 — is
+  // evaluated in the same instruction stream, keeping the gain after every sample (gring).  The AGC does not depend on
+  // the timing loop, only on the lock flag, so the look-ahead is exact unless the symbol processing of round r flips
+  // that flag (a few times per burst) — then it is thrown away and redone.  Round r+1 then just picks gring[nseg-1].
+  bool pre_ok = false;     // gring / the y ring already hold samples pos .. pos+WS_SPEC-1
 
   while (true) {
     ws_bar_sync(WS_BAR_DATA);              // the producer's refill for this round is complete and visible
@@ -692,8 +693,9 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
     const int nmin = __reduce_min_sync(0xffffffffu, nseg);
     const float bw_eff = (a.flags & FLAG_AGC_LOCKED) ? 0.0f : bw;   // (!locked as f32) * (1-|y|) * bw   agc.rs:74
     // use the look-ahead only if every lane that works this round has one (uniform start index keeps the loop simple)
-    const bool use_pre = __all_sync(0xffffffffu, nseg == 0 || (pre_ok && nseg >= WS_SPEC));
-    float g = use_pre ? g_pre : a.g;
+    const bool use_pre = __all_sync(0xffffffffu, nseg == 0 || pre_ok);
+    float g = a.g;
+    if (use_pre && nseg > 0) g = gring[(min(nseg, WS_SPEC) - 1) * 32 + lane];
     int k = use_pre ? WS_SPEC : 0;
     uint32_t od = (((pos + (uint32_t)k) << 7) & 0x3f80u) | ((uint32_t)lane << 2);   // d ring: 128 slots
     uint32_t oy = (((pos + (uint32_t)k) << 7) & 0x1f80u) | ((uint32_t)lane << 2);   // y ring: 64 slots + mirror
@@ -763,7 +765,7 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
             if ((j * FAST_NTAPS) / WS_SPEC == i) {   // compile-time schedule: look-ahead sample j rides with tap i
               const float y = FMUL(dsp[j], gs);
               gs = fminf(fmaxf(FADD(gs, FMUL(FSUB(1.0f, fabsf(y)), bw_eff)), gmin), gmax);
-              if (spec) sts_f32_mirrored(y_base + sy, y);
+              if (spec) { sts_f32_mirrored(y_base + sy, y); gring[j * 32 + lane] = gs; }
               sy = (sy + 128u) & 0x1fffu;
             }
           }
@@ -791,7 +793,7 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
       }
     }
     // the look-ahead stands if this lane is not parked and its AGC lock flag is what the look-ahead assumed
-    if (spec && pend == 0u && (a.flags & FLAG_AGC_LOCKED) == lock_before) { pre_ok = true; g_pre = gs; }
+    if (spec && pend == 0u && (a.flags & FLAG_AGC_LOCKED) == lock_before) pre_ok = true;
   }
 
   if (!valid || len == 0u) return;
