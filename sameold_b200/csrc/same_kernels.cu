@@ -481,12 +481,14 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
 // ----------------------------------------------------------------------------------------------------------------
 #define WS_DRING 128       // d ring slots of the warp-specialised kernel
 #define WS_SPEC 22         // look-ahead samples: 42 taps + 22 new samples just fit the 64-slot y ring; covers most whole segments
-#define WS_BAR_DATA 1
-#define WS_BAR_POS 2
-__device__ __forceinline__ void ws_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void ws_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+#define WS_BAR_DATA 1      // producer -> consumer            (64 threads)
+#define WS_BAR_POS 2       // consumer -> producer, look-ahead (96 threads)
+#define WS_BAR_LA 3        // look-ahead -> consumer          (64 threads)
+#define WS_THREADS 96
+__device__ __forceinline__ void ws_bar_sync(int id, int n = 64) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void ws_bar_arrive(int id, int n = 64) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-__global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ SameParams p,
+__global__ void __launch_bounds__(WS_THREADS) same_rx_ws_kernel(const __grid_constant__ SameParams p,
                                                         const __grid_constant__ SameTaps2 taps,
                                                         const int16_t* __restrict__ samples,
                                                         const unsigned long long* __restrict__ offsets,
@@ -498,10 +500,12 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
   __shared__ volatile uint32_t sh_rp[32];    // samples produced per lane (written by the producer warp)
   __shared__ volatile uint32_t sh_pos[32];   // samples consumed per lane (written by the consumer warp)
   __shared__ volatile uint32_t sh_done;      // consumer -> producer: no more rounds
+  __shared__ volatile float sh_la_g[32];     // consumer -> look-ahead: AGC gain at pos
+  __shared__ volatile uint32_t sh_la_rq[32]; // consumer -> look-ahead: bit 0 look-ahead wanted, bit 1 AGC locked
 
   const SameLayout& L = p.layout;
   const int lane = threadIdx.x & 31;
-  const int role = threadIdx.x >> 5;         // 0 consumer, 1 producer
+  const int role = threadIdx.x >> 5;         // 0 consumer, 1 producer, 2 look-ahead
   const uint32_t s = blockIdx.x * lanes + lane;
   const bool valid = (uint32_t)lane < lanes && s < p.n_streams;
   const uint32_t sidx = valid ? s : 0u;
@@ -513,8 +517,10 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
   const int16_t* src = (samples != nullptr && valid) ? samples + offsets[s] : nullptr;
 
   // ---- shared set-up (both warps) ----
-  for (int i = role; i < WS_DRING; i += 2) dring[i * 32 + lane] = 0.0f;   // stale slots are read, never used: keep them finite
-  if (role == 0) {
+  for (int i = role; i < WS_DRING; i += 3) dring[i * 32 + lane] = 0.0f;   // stale slots are read, never used: keep them finite
+  if (role == 2) {
+    sh_la_rq[lane] = 0u;
+  } else if (role == 0) {
     for (int i = 0; i < FAST_NTAPS; ++i) {   // demod window -> y ring slots of samples -42..-1 (and mirrors)
       const float v = __uint_as_float(LANE_ST(st, L, L.win + i));
       const int slot = (i - FAST_NTAPS) & (FAST_RING - 1);
@@ -560,7 +566,7 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
     bool first = true;
     while (true) {
       if (!first) {
-        ws_bar_sync(WS_BAR_POS);           // the consumer finished a segment and published pos
+        ws_bar_sync(WS_BAR_POS, WS_THREADS);   // the consumer finished a segment and published pos
         if (sh_done) break;
       }
       first = false;
@@ -657,30 +663,66 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
     return;
   }
 
+  const float bw = p.agc_bw, gmin = p.agc_min, gmax = p.agc_max;
+  const uint32_t d_base = smem_u32(dring), y_base = smem_u32(yring);
+  const uint32_t g_base = smem_u32(gring) + ((uint32_t)lane << 2);
+
+  if (role == 2) {
+    // ============================================== look-ahead ==============================================
+    // While the consumer runs the matched filters, timing loop and symbol stages of round r, this warp evaluates the
+    // AGC recurrence of the next WS_SPEC samples — normally the whole segment of round r+1 — into the y ring, keeping
+    // the gain after every sample (gring).  The AGC does not depend on the timing loop, only on the lock flag, so the
+    // look-ahead is exact unless the symbol processing of round r flips that flag (a few times per burst) or parks
+    // the lane; the consumer then throws it away and runs the recurrence itself.
+    ws_bar_arrive(WS_BAR_LA);                // nothing to wait for in the first round
+    while (true) {
+      ws_bar_sync(WS_BAR_POS, WS_THREADS);
+      if (sh_done) break;
+      const uint32_t rq = sh_la_rq[lane];
+      if (__any_sync(0xffffffffu, (rq & 1u) != 0u)) {
+        // lanes that did not ask run along and store too: their slots pos .. pos+21 hold samples nobody has produced
+        // yet (they alias samples pos-64 .. pos-43, older than the 42-tap window) and are rewritten before use
+        const float bw_eff = (rq & 2u) ? 0.0f : bw;
+        float gs = sh_la_g[lane];
+        const uint32_t lpos = sh_pos[lane];
+        uint32_t sd = ((lpos << 7) & 0x3f80u) | ((uint32_t)lane << 2);
+        uint32_t sy = ((lpos << 7) & 0x1f80u) | ((uint32_t)lane << 2);
+        float dsp[WS_SPEC];
+#pragma unroll
+        for (int j = 0; j < WS_SPEC; ++j) { dsp[j] = lds_f32(d_base + sd); sd = (sd + 128u) & 0x3fffu; }
+#pragma unroll
+        for (int j = 0; j < WS_SPEC; ++j) {
+          const float y = FMUL(dsp[j], gs);                                                 // agc.rs:73
+          gs = fminf(fmaxf(FADD(gs, FMUL(FSUB(1.0f, fabsf(y)), bw_eff)), gmin), gmax);      // agc.rs:74-75
+          sts_f32_mirrored(y_base + sy, y);
+          sts_f32(g_base + (uint32_t)(j * 128), gs);
+          sy = (sy + 128u) & 0x1fffu;
+        }
+      }
+      __threadfence_block();
+      ws_bar_arrive(WS_BAR_LA);
+    }
+    return;
+  }
+
   // ================================================= consumer =================================================
   Lane a;
   lane_load(a, p, st, s);
-  const float bw = p.agc_bw, gmin = p.agc_min, gmax = p.agc_max;
   const float2 one2 = make_float2(p.f_one, p.f_one), negz2 = make_float2(p.f_negzero, p.f_negzero);
-  const uint32_t d_base = smem_u32(dring), y_base = smem_u32(yring);
 
   uint32_t pos = 0;
   int cfire = fire_clock(a.until, a.clock);
   uint32_t pend = 0;       // SYM_BYTE_READY | SYM_ADJUSTED while parked (byte-phase alignment, see same_rx_fast_kernel)
   uint32_t round_ctr = 0;
-  // Speculative look-ahead: while the matched filters of round r run (a 42-deep dependent chain that leaves most issue
-  // slots empty), the AGC recurrence of the next WS_SPEC samples — normally the whole segment of round r+1 — is
-  // evaluated in the same instruction stream, keeping the gain after every sample (gring).  The AGC does not depend on
-  // the timing loop, only on the lock flag, so the look-ahead is exact unless the symbol processing of round r flips
-  // that flag (a few times per burst) — then it is thrown away and redone.  Round r+1 then just picks gring[nseg-1].
-  bool pre_ok = false;     // gring / the y ring already hold samples pos .. pos+WS_SPEC-1
+  bool pre_ok = false;     // gring / the y ring already hold samples pos .. pos+WS_SPEC-1 (look-ahead warp)
 
   while (true) {
     ws_bar_sync(WS_BAR_DATA);              // the producer's refill for this round is complete and visible
+    ws_bar_sync(WS_BAR_LA);                // ... and so is the look-ahead
     if (!__any_sync(0xffffffffu, pos < len || pend != 0u)) {
       if (lane == 0) sh_done = 1u;
       __threadfence_block();
-      ws_bar_arrive(WS_BAR_POS);
+      ws_bar_arrive(WS_BAR_POS, WS_THREADS);
       break;
     }
     // ---------------- segment: AGC over this lane's samples up to its next TED instant (A2, A3) ----------------
@@ -695,7 +737,7 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
     // use the look-ahead only if every lane that works this round has one (uniform start index keeps the loop simple)
     const bool use_pre = __all_sync(0xffffffffu, nseg == 0 || pre_ok);
     float g = a.g;
-    if (use_pre && nseg > 0) g = gring[(min(nseg, WS_SPEC) - 1) * 32 + lane];
+    if (use_pre && nseg > 0) g = lds_f32(g_base + (uint32_t)((min(nseg, WS_SPEC) - 1) << 7));
     int k = use_pre ? WS_SPEC : 0;
     uint32_t od = (((pos + (uint32_t)k) << 7) & 0x3f80u) | ((uint32_t)lane << 2);   // d ring: 128 slots
     uint32_t oy = (((pos + (uint32_t)k) << 7) & 0x1f80u) | ((uint32_t)lane << 2);   // y ring: 64 slots + mirror
@@ -733,42 +775,26 @@ __global__ void __launch_bounds__(64) same_rx_ws_kernel(const __grid_constant__ 
     pre_ok = false;
     pos += (uint32_t)nseg;
     a.clock += nseg;
-    sh_pos[lane] = pos;      // lets the producer reuse the ring slots behind pos
-    __threadfence_block();
-    ws_bar_arrive(WS_BAR_POS);
     const bool fire = (nseg > 0) && (a.clock == cfire);
-    bool have_sym = false;
     const uint32_t lock_before = a.flags & FLAG_AGC_LOCKED;
-    bool spec = false;
-    float gs = a.g;
+    // ask for the look-ahead of the next segment when this lane is at a TED instant and has the samples for it
+    const bool spec = fire && (rp - pos) >= (uint32_t)WS_SPEC && (len - pos) >= (uint32_t)WS_SPEC;
+    sh_pos[lane] = pos;      // lets the producer reuse the ring slots behind pos
+    sh_la_g[lane] = a.g;
+    sh_la_rq[lane] = (spec ? 1u : 0u) | (lock_before ? 2u : 0u);
+    __threadfence_block();
+    ws_bar_arrive(WS_BAR_POS, WS_THREADS);
+    bool have_sym = false;
     if (__any_sync(0xffffffffu, fire)) {
-      // ---------------- TED instant: matched filters (A4) with packed exact f32 ops (see same_rx_fast_kernel),
-      //                  with the look-ahead AGC of samples pos .. pos+WS_SPEC-1 woven between the taps ----------------
-      // ptxas keeps shared-memory loads and stores in program order (it cannot prove the ring slots distinct), so the
-      // two independent dependency chains are interleaved here in the source: one AGC step every 2-3 taps.
-      spec = fire && (rp - pos) >= (uint32_t)WS_SPEC && (len - pos) >= (uint32_t)WS_SPEC;
+      // ---------------- TED instant: matched filters (A4) with packed exact f32 ops (see same_rx_fast_kernel) ----------------
       float soft;
       {
-        float dsp[WS_SPEC];
-        uint32_t sd = ((pos << 7) & 0x3f80u) | ((uint32_t)lane << 2);
-        uint32_t sy = ((pos << 7) & 0x1f80u) | ((uint32_t)lane << 2);
-#pragma unroll
-        for (int j = 0; j < WS_SPEC; ++j) { dsp[j] = lds_f32(d_base + sd); sd = (sd + 128u) & 0x3fffu; }
         int nslot = (int)((pos - 1u) & (FAST_RING - 1));
         if (nslot < FAST_NTAPS - 1) nslot += FAST_RING;
         const float* yp = yring + nslot * 32 + lane;
         float2 am = make_float2(0.0f, 0.0f), as = make_float2(0.0f, 0.0f);
 #pragma unroll
         for (int i = 0; i < FAST_NTAPS; ++i) {
-#pragma unroll
-          for (int j = 0; j < WS_SPEC; ++j) {
-            if ((j * FAST_NTAPS) / WS_SPEC == i) {   // compile-time schedule: look-ahead sample j rides with tap i
-              const float y = FMUL(dsp[j], gs);
-              gs = fminf(fmaxf(FADD(gs, FMUL(FSUB(1.0f, fabsf(y)), bw_eff)), gmin), gmax);
-              if (spec) { sts_f32_mirrored(y_base + sy, y); gring[j * 32 + lane] = gs; }
-              sy = (sy + 128u) & 0x1fffu;
-            }
-          }
           const float v = yp[-i * 32];
           const float4 t = tapsm[i];
           const float2 vv = make_float2(v, v);
@@ -841,7 +867,7 @@ extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps,
     if (force_generic == 2)
       same_dev::same_rx_fast_kernel<<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes);
     else
-      same_dev::same_rx_ws_kernel<<<fblocks, 64, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes);
+      same_dev::same_rx_ws_kernel<<<fblocks, WS_THREADS, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes);
   } else if (p->ntaps <= 64 && p->dc_len <= 16) {
     const size_t smem = (size_t)(64 + 2 * 16) * 32 * sizeof(float);
     same_dev::same_rx_generic_kernel<64, 16><<<blocks, 32, smem, stream>>>(*p, *taps, d_samples, d_offsets, d_lengths);
