@@ -357,7 +357,9 @@ int same_engine_create(const same_config* cfg_in, int device, uint32_t n_streams
       uint32_t v = (uint32_t)atoi(lw);
       if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) e->lanes_per_warp = v;
     }
-    if (const char* kv = getenv("SAME_KERNEL")) e->kernel_auto = atoi(kv) == 2 ? 2 : 0;
+    if (const char* kv = getenv("SAME_KERNEL")) {   // diagnostic: ws | 2 (single warp) | pipe
+      e->kernel_auto = atoi(kv) == 2 ? 2 : (strcmp(kv, "pipe") == 0 || atoi(kv) == 3) ? 3 : 0;
+    }
   }
   p.spt = sps / 2.0f;                                                         // symsync.rs:146
   {

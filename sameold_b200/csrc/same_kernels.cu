@@ -488,6 +488,138 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
 __device__ __forceinline__ void ws_bar_sync(int id, int n = 64) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void ws_bar_arrive(int id, int n = 64) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+// Producer warp of the warp-specialised kernels: raw s16 -> exact DC-blocked f32 into the d ring (A0, A1).  Each round:
+// wait for the consumer's position (bar_pos), refill every lane that has room for a whole 32-sample chunk, publish rp,
+// arrive on bar_data.  Stores the DC-blocker state of the lane when the consumer signals the end.
+__device__ __forceinline__ void ws_producer(const SameParams& p, uint32_t* st, const int16_t* src, const uint32_t len,
+                                            const int lane, const bool valid, float* dring, volatile uint32_t* sh_rp,
+                                            volatile uint32_t* sh_pos, volatile uint32_t* sh_done, const int bar_pos,
+                                            const int bar_pos_n, const int bar_data, const int bar_data_n) {
+  const SameLayout& L = p.layout;
+  const bool src_aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+  uint32_t rawh[FAST_DCL / 2];   // last 16 raw samples, packed pairs, oldest first   (ff window, dcblock.rs:63)
+  int s1h[FAST_DCL];             // S1 = 16 * ma0 for the last 16 samples            (fb window)
+  int S1 = __float2int_rn(__uint_as_float(LANE_ST(st, L, F_DC_FFSUM)));
+  int S2 = __float2int_rn(__uint_as_float(LANE_ST(st, L, F_DC_FBSUM)) * 16.0f);
+#pragma unroll
+  for (int i = 0; i < FAST_DCL / 2; ++i) {
+    int lo = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_ff + 2 * i)));
+    int hi = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_ff + 2 * i + 1)));
+    rawh[i] = ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16);
+  }
+#pragma unroll
+  for (int i = 0; i < FAST_DCL; ++i) s1h[i] = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_fb + i)) * 16.0f);
+
+  uint32_t rp = 0;
+  bool dc_windows_stored = false;
+  int4 nx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) nx[i] = make_int4(0, 0, 0, 0);
+  bool pf_ok = src != nullptr && src_aligned && len >= (uint32_t)FAST_CHUNK;
+  if (pf_ok) {
+    const int4* q = reinterpret_cast<const int4*>(src);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) nx[i] = __ldg(q + i);
+  }
+  bool first = true;
+  while (true) {
+    if (!first) {
+      ws_bar_sync(bar_pos, bar_pos_n);   // the consumer finished a segment and published pos
+      if (*sh_done) break;
+    }
+    first = false;
+    const uint32_t cpos = sh_pos[lane];
+    // every lane with room for a whole chunk takes one: afterwards it holds >= 32 samples, more than any segment
+    const bool take = (rp < len) && (rp - cpos) <= (uint32_t)(WS_DRING - FAST_CHUNK);
+    const uint32_t nnew = take ? min((uint32_t)FAST_CHUNK, len - rp) : 0u;
+    if (nnew == FAST_CHUNK) {
+      uint32_t cur[FAST_CHUNK / 2];
+      if (pf_ok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { cur[4 * i] = nx[i].x; cur[4 * i + 1] = nx[i].y; cur[4 * i + 2] = nx[i].z; cur[4 * i + 3] = nx[i].w; }
+      } else {
+#pragma unroll
+        for (int i = 0; i < FAST_CHUNK / 2; ++i) {
+          const uint32_t lo = src ? (uint32_t)(uint16_t)src[rp + 2 * i] : 0u;
+          const uint32_t hi = src ? (uint32_t)(uint16_t)src[rp + 2 * i + 1] : 0u;
+          cur[i] = lo | (hi << 16);
+        }
+      }
+      pf_ok = src != nullptr && src_aligned && (len - rp) >= 2u * FAST_CHUNK;
+      if (pf_ok) {
+        const int4* q = reinterpret_cast<const int4*>(src + rp + FAST_CHUNK);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nx[i] = __ldg(q + i);
+      }
+      float* dst = dring + (rp & (WS_DRING - 1)) * 32 + lane;  // rp % 32 == 0: the chunk never wraps
+#pragma unroll
+      for (int i = 0; i < FAST_CHUNK; ++i) {
+        const int x = s16_at(cur, i);
+        const int x16 = (i < FAST_DCL) ? s16_at(rawh, i) : s16_at(cur, i - FAST_DCL);
+        const int x15 = (i < FAST_DCL - 1) ? s16_at(rawh, i + 1) : s16_at(cur, i - (FAST_DCL - 1));
+        S1 += x - x16;                    // ff: moving_sum += input - aged          dcblock.rs:106
+        S2 += S1 - s1h[i & 15];           // fb: moving_sum += ma0 - aged            dcblock.rs:106
+        s1h[i & 15] = S1;
+        const int D = (x15 << 8) - S2;    // 256 * (sig - ma1)                       dcblock.rs:48
+        dst[i * 32] = (float)D * 0.00390625f;
+      }
+#pragma unroll
+      for (int i = 0; i < FAST_DCL / 2; ++i) rawh[i] = cur[FAST_CHUNK / 2 - FAST_DCL / 2 + i];
+      rp += FAST_CHUNK;
+    } else if (nnew) {
+      uint32_t cur[FAST_CHUNK / 2];
+#pragma unroll
+      for (int i = 0; i < FAST_CHUNK / 2; ++i) cur[i] = 0u;
+#pragma unroll
+      for (int i = 0; i < FAST_CHUNK; ++i) {
+        const uint32_t v = (src && i < (int)nnew) ? (uint32_t)(uint16_t)src[rp + i] : 0u;
+        cur[i >> 1] |= (i & 1) ? (v << 16) : v;
+      }
+      float* dst = dring + (rp & (WS_DRING - 1)) * 32 + lane;
+#pragma unroll
+      for (int i = 0; i < FAST_CHUNK; ++i) {
+        if (i < (int)nnew) {
+          const int x = s16_at(cur, i);
+          const int x16 = (i < FAST_DCL) ? s16_at(rawh, i) : s16_at(cur, i - FAST_DCL);
+          const int x15 = (i < FAST_DCL - 1) ? s16_at(rawh, i + 1) : s16_at(cur, i - (FAST_DCL - 1));
+          S1 += x - x16;
+          S2 += S1 - s1h[i & 15];
+          s1h[i & 15] = S1;
+          const int D = (x15 << 8) - S2;
+          dst[i * 32] = (float)D * 0.00390625f;
+        }
+      }
+      // final DC windows, rotated so that index 0 is the oldest sample again (see same_rx_fast_kernel)
+#pragma unroll
+      for (int i = 0; i < FAST_DCL; ++i) {
+        if (i >= (int)nnew) LANE_ST(st, L, L.dc_ff + ((uint32_t)i - nnew)) = __float_as_uint((float)s16_at(rawh, i));
+        LANE_ST(st, L, L.dc_fb + (((uint32_t)i - nnew) & 15u)) = __float_as_uint((float)s1h[i] * 0.0625f);
+      }
+#pragma unroll
+      for (int i = 0; i < FAST_CHUNK; ++i) {
+        if (i < (int)nnew && i + FAST_DCL >= (int)nnew)
+          LANE_ST(st, L, L.dc_ff + ((uint32_t)(i + FAST_DCL) - nnew)) = __float_as_uint((float)s16_at(cur, i));
+      }
+      dc_windows_stored = true;
+      rp += nnew;
+    }
+    sh_rp[lane] = rp;
+    __threadfence_block();             // d values and rp visible before the consumer is released
+    ws_bar_arrive(bar_data, bar_data_n);
+  }
+  if (valid && len != 0u) {
+    LANE_ST(st, L, F_DC_FFSUM) = __float_as_uint((float)S1);
+    LANE_ST(st, L, F_DC_FBSUM) = __float_as_uint((float)S2 * 0.0625f);
+    if (!dc_windows_stored) {
+#pragma unroll
+      for (int i = 0; i < FAST_DCL; ++i) {
+        LANE_ST(st, L, L.dc_ff + i) = __float_as_uint((float)s16_at(rawh, i));
+        LANE_ST(st, L, L.dc_fb + i) = __float_as_uint((float)s1h[i] * 0.0625f);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(WS_THREADS) same_rx_ws_kernel(const __grid_constant__ SameParams p,
                                                         const __grid_constant__ SameTaps2 taps,
                                                         const int16_t* __restrict__ samples,
@@ -537,129 +669,7 @@ __global__ void __launch_bounds__(WS_THREADS) same_rx_ws_kernel(const __grid_con
   __syncthreads();
 
   if (role == 1) {
-    // =============================================== producer ===============================================
-    const bool src_aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
-    uint32_t rawh[FAST_DCL / 2];   // last 16 raw samples, packed pairs, oldest first   (ff window, dcblock.rs:63)
-    int s1h[FAST_DCL];             // S1 = 16 * ma0 for the last 16 samples            (fb window)
-    int S1 = __float2int_rn(__uint_as_float(LANE_ST(st, L, F_DC_FFSUM)));
-    int S2 = __float2int_rn(__uint_as_float(LANE_ST(st, L, F_DC_FBSUM)) * 16.0f);
-#pragma unroll
-    for (int i = 0; i < FAST_DCL / 2; ++i) {
-      int lo = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_ff + 2 * i)));
-      int hi = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_ff + 2 * i + 1)));
-      rawh[i] = ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16);
-    }
-#pragma unroll
-    for (int i = 0; i < FAST_DCL; ++i) s1h[i] = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_fb + i)) * 16.0f);
-
-    uint32_t rp = 0;
-    bool dc_windows_stored = false;
-    int4 nx[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) nx[i] = make_int4(0, 0, 0, 0);
-    bool pf_ok = src != nullptr && src_aligned && len >= (uint32_t)FAST_CHUNK;
-    if (pf_ok) {
-      const int4* q = reinterpret_cast<const int4*>(src);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) nx[i] = __ldg(q + i);
-    }
-    bool first = true;
-    while (true) {
-      if (!first) {
-        ws_bar_sync(WS_BAR_POS, WS_THREADS);   // the consumer finished a segment and published pos
-        if (sh_done) break;
-      }
-      first = false;
-      const uint32_t cpos = sh_pos[lane];
-      // every lane with room for a whole chunk takes one: afterwards it holds >= 32 samples, more than any segment
-      const bool take = (rp < len) && (rp - cpos) <= (uint32_t)(WS_DRING - FAST_CHUNK);
-      const uint32_t nnew = take ? min((uint32_t)FAST_CHUNK, len - rp) : 0u;
-      if (nnew == FAST_CHUNK) {
-        uint32_t cur[FAST_CHUNK / 2];
-        if (pf_ok) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { cur[4 * i] = nx[i].x; cur[4 * i + 1] = nx[i].y; cur[4 * i + 2] = nx[i].z; cur[4 * i + 3] = nx[i].w; }
-        } else {
-#pragma unroll
-          for (int i = 0; i < FAST_CHUNK / 2; ++i) {
-            const uint32_t lo = src ? (uint32_t)(uint16_t)src[rp + 2 * i] : 0u;
-            const uint32_t hi = src ? (uint32_t)(uint16_t)src[rp + 2 * i + 1] : 0u;
-            cur[i] = lo | (hi << 16);
-          }
-        }
-        pf_ok = src != nullptr && src_aligned && (len - rp) >= 2u * FAST_CHUNK;
-        if (pf_ok) {
-          const int4* q = reinterpret_cast<const int4*>(src + rp + FAST_CHUNK);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) nx[i] = __ldg(q + i);
-        }
-        float* dst = dring + (rp & (WS_DRING - 1)) * 32 + lane;  // rp % 32 == 0: the chunk never wraps
-#pragma unroll
-        for (int i = 0; i < FAST_CHUNK; ++i) {
-          const int x = s16_at(cur, i);
-          const int x16 = (i < FAST_DCL) ? s16_at(rawh, i) : s16_at(cur, i - FAST_DCL);
-          const int x15 = (i < FAST_DCL - 1) ? s16_at(rawh, i + 1) : s16_at(cur, i - (FAST_DCL - 1));
-          S1 += x - x16;                    // ff: moving_sum += input - aged          dcblock.rs:106
-          S2 += S1 - s1h[i & 15];           // fb: moving_sum += ma0 - aged            dcblock.rs:106
-          s1h[i & 15] = S1;
-          const int D = (x15 << 8) - S2;    // 256 * (sig - ma1)                       dcblock.rs:48
-          dst[i * 32] = (float)D * 0.00390625f;
-        }
-#pragma unroll
-        for (int i = 0; i < FAST_DCL / 2; ++i) rawh[i] = cur[FAST_CHUNK / 2 - FAST_DCL / 2 + i];
-        rp += FAST_CHUNK;
-      } else if (nnew) {
-        uint32_t cur[FAST_CHUNK / 2];
-#pragma unroll
-        for (int i = 0; i < FAST_CHUNK / 2; ++i) cur[i] = 0u;
-#pragma unroll
-        for (int i = 0; i < FAST_CHUNK; ++i) {
-          const uint32_t v = (src && i < (int)nnew) ? (uint32_t)(uint16_t)src[rp + i] : 0u;
-          cur[i >> 1] |= (i & 1) ? (v << 16) : v;
-        }
-        float* dst = dring + (rp & (WS_DRING - 1)) * 32 + lane;
-#pragma unroll
-        for (int i = 0; i < FAST_CHUNK; ++i) {
-          if (i < (int)nnew) {
-            const int x = s16_at(cur, i);
-            const int x16 = (i < FAST_DCL) ? s16_at(rawh, i) : s16_at(cur, i - FAST_DCL);
-            const int x15 = (i < FAST_DCL - 1) ? s16_at(rawh, i + 1) : s16_at(cur, i - (FAST_DCL - 1));
-            S1 += x - x16;
-            S2 += S1 - s1h[i & 15];
-            s1h[i & 15] = S1;
-            const int D = (x15 << 8) - S2;
-            dst[i * 32] = (float)D * 0.00390625f;
-          }
-        }
-        // final DC windows, rotated so that index 0 is the oldest sample again (see same_rx_fast_kernel)
-#pragma unroll
-        for (int i = 0; i < FAST_DCL; ++i) {
-          if (i >= (int)nnew) LANE_ST(st, L, L.dc_ff + ((uint32_t)i - nnew)) = __float_as_uint((float)s16_at(rawh, i));
-          LANE_ST(st, L, L.dc_fb + (((uint32_t)i - nnew) & 15u)) = __float_as_uint((float)s1h[i] * 0.0625f);
-        }
-#pragma unroll
-        for (int i = 0; i < FAST_CHUNK; ++i) {
-          if (i < (int)nnew && i + FAST_DCL >= (int)nnew)
-            LANE_ST(st, L, L.dc_ff + ((uint32_t)(i + FAST_DCL) - nnew)) = __float_as_uint((float)s16_at(cur, i));
-        }
-        dc_windows_stored = true;
-        rp += nnew;
-      }
-      sh_rp[lane] = rp;
-      __threadfence_block();             // d values and rp visible before the consumer is released
-      ws_bar_arrive(WS_BAR_DATA);
-    }
-    if (valid && len != 0u) {
-      LANE_ST(st, L, F_DC_FFSUM) = __float_as_uint((float)S1);
-      LANE_ST(st, L, F_DC_FBSUM) = __float_as_uint((float)S2 * 0.0625f);
-      if (!dc_windows_stored) {
-#pragma unroll
-        for (int i = 0; i < FAST_DCL; ++i) {
-          LANE_ST(st, L, L.dc_ff + i) = __float_as_uint((float)s16_at(rawh, i));
-          LANE_ST(st, L, L.dc_fb + i) = __float_as_uint((float)s1h[i] * 0.0625f);
-        }
-      }
-    }
+    ws_producer(p, st, src, len, lane, valid, dring, sh_rp, sh_pos, &sh_done, WS_BAR_POS, WS_THREADS, WS_BAR_DATA, 64);
     return;
   }
 
@@ -828,6 +838,278 @@ __global__ void __launch_bounds__(WS_THREADS) same_rx_ws_kernel(const __grid_con
     LANE_ST(st, L, L.win + i) = __float_as_uint(yring[((int)(pos + i - FAST_NTAPS) & (FAST_RING - 1)) * 32 + lane]);
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// Pipelined kernel: the receiver of 32 streams spread over four warps (one per scheduler of the SM), so that the
+// per-round critical path is "segment bookkeeping -> one matched filter -> timing loop -> squelch / byte path".
+//
+//   warp P   producer   raw s16 -> exact DC-blocked f32 (d ring)                                          A0, A1
+//   warp A   AGC        free-running gain recurrence, up to PK_LEAD samples ahead of the consumer:
+//                       y ring + gain ring (gain after every sample)                                       A2, A3
+//   warp S   space      the space matched filter and its magnitude at the consumer's TED instant          A4
+//   warp F   consumer   picks the gain that belongs to its position, mark matched filter and magnitude,
+//                       timing loop, squelch, equalizer, framer, transport                                 A4-A9
+//
+// The AGC depends on the consumer only through the lock flag (agc.rs:74), so it runs ahead speculatively and exactly:
+// whenever the consumer's flag flips, or the AGC warp has not got far enough, the consumer runs the recurrence itself
+// with the same arithmetic (fallback below) and tells the AGC warp to restart from its position and gain.
+// Lockstep rounds on three named barriers:
+//   F: sync DONE -> segment -> publish (pos, gain, flag, restart) -> arrive POS -> mark -> sync SPACE -> TED, symbol
+//   S: sync POS -> space filter at pos -> arrive SPACE            A, P: sync POS -> work -> arrive DONE
+// ----------------------------------------------------------------------------------------------------------------
+#define PK_THREADS 128
+#define PK_YRING 128       // y ring slots; slots 0..40 are mirrored at 128..168 so a 42-tap window never wraps
+#define PK_YMIRROR (FAST_NTAPS - 1)
+#define PK_GRING 64        // gain ring slots
+#define PK_LEAD 48         // the AGC warp stays at most this far ahead of the consumer
+#define PK_ADV 32          // ... and advances at most this much per round
+#define PK_BAR_POS 1       // F -> S, A, P     (128 threads)
+#define PK_BAR_DONE 2      // A, P -> F        (96 threads)
+#define PK_BAR_SPACE 3     // S -> F           (64 threads)
+
+__device__ __forceinline__ void pk_sts_y(uint32_t y_lane, uint32_t sample, float v, bool act) {
+  const uint32_t slot = sample & (PK_YRING - 1);
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %2, 0;\n\tsetp.lt.and.u32 q, %3, 41, p;\n\t"
+      "@p st.shared.f32 [%0], %1;\n\t@q st.shared.f32 [%0+16384], %1;\n\t}" ::"r"(y_lane + (slot << 7)),
+      "f"(v), "r"((uint32_t)act), "r"(slot)
+      : "memory");
+}
+__device__ __forceinline__ void pk_sts_pred(uint32_t addr, float v, bool act) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.f32 [%0], %1;\n\t}" ::"r"(addr), "f"(v),
+               "r"((uint32_t)act)
+               : "memory");
+}
+
+// |matched filter output| over the 42 samples that end at sample index `end` (exclusive); taps from the constant bank.
+// One rounded multiply and one rounded add per component and tap, newest sample first (demod.rs:156-163).
+__device__ __forceinline__ float pk_mag(const float* yring, const float2* __restrict__ h, const int lane,
+                                        const uint32_t end) {
+  int nslot = (int)((end - 1u) & (PK_YRING - 1));
+  if (nslot < FAST_NTAPS - 1) nslot += PK_YRING;
+  const float* yp = yring + nslot * 32 + lane;
+  float re = 0.0f, im = 0.0f;
+#pragma unroll
+  for (int i = 0; i < FAST_NTAPS; ++i) {
+    const float v = yp[-i * 32];
+    re = FADD(re, FMUL(v, h[i].x));
+    im = FADD(im, FMUL(v, h[i].y));
+  }
+  return hypot_fixed(re, im);
+}
+
+__global__ void __launch_bounds__(PK_THREADS) same_rx_pipe_kernel(const __grid_constant__ SameParams p,
+                                                                  const __grid_constant__ SameTaps2 taps,
+                                                                  const int16_t* __restrict__ samples,
+                                                                  const unsigned long long* __restrict__ offsets,
+                                                                  const uint32_t* __restrict__ lengths,
+                                                                  const uint32_t lanes) {
+  __shared__ float dring[WS_DRING * 32];
+  __shared__ float yring[(PK_YRING + PK_YMIRROR) * 32];
+  __shared__ float gring[PK_GRING * 32];
+  __shared__ volatile float sh_space[32];    // |space filter| at pos                  (S)
+  __shared__ volatile uint32_t sh_rp[32];    // samples produced per lane              (P)
+  __shared__ volatile uint32_t sh_apos[32];  // samples AGC'd per lane                 (A)
+  __shared__ volatile uint32_t sh_pos[32];   // samples consumed per lane              (F)
+  __shared__ volatile float sh_g[32];        // AGC gain at pos                        (F)
+  __shared__ volatile uint32_t sh_rq[32];    // bit 0 restart the AGC at pos, bit 1 AGC locked   (F)
+  __shared__ volatile uint32_t sh_frp[32];   // rp as the consumer saw it at the top of the round  (F)
+  __shared__ volatile uint32_t sh_done;
+
+  const SameLayout& L = p.layout;
+  const int lane = threadIdx.x & 31;
+  enum { R_F = 0, R_S = 1, R_A = 2, R_P = 3 };
+  const int role = threadIdx.x >> 5;
+  const uint32_t s = blockIdx.x * lanes + lane;
+  const bool valid = (uint32_t)lane < lanes && s < p.n_streams;
+  const uint32_t sidx = valid ? s : 0u;
+  uint32_t* st = p.state32 + sidx;
+  StreamBlob* blob = p.blobs + sidx;
+
+  const uint32_t len = valid ? lengths[s] : 0u;
+  if (__syncthreads_and(len == 0u)) return;   // block-uniform
+  const int16_t* src = (samples != nullptr && valid) ? samples + offsets[s] : nullptr;
+
+  // ---- shared set-up ----
+  for (int i = role; i < WS_DRING; i += 4) dring[i * 32 + lane] = 0.0f;   // stale slots are read, never used: keep them finite
+  if (role == R_F) {
+    for (int i = 0; i < FAST_NTAPS; ++i) {   // demod window -> y ring slots of samples -42..-1 (86..127: no mirror)
+      const float v = __uint_as_float(LANE_ST(st, L, L.win + i));
+      yring[((i - FAST_NTAPS) & (PK_YRING - 1)) * 32 + lane] = v;
+    }
+    sh_pos[lane] = 0u;
+    if (lane == 0) sh_done = 0u;
+  } else if (role == R_A) {
+    sh_apos[lane] = 0u;
+    for (int i = 0; i < PK_YRING - FAST_NTAPS; ++i) yring[i * 32 + lane] = 0.0f;   // keep never-written slots finite
+  } else if (role == R_S) {
+    for (int i = 0; i < PK_YMIRROR; ++i) yring[(PK_YRING + i) * 32 + lane] = 0.0f;
+    sh_space[lane] = 0.0f;
+  } else {
+    sh_rp[lane] = 0u;
+  }
+  __syncthreads();
+
+  if (role == R_P) {
+    ws_producer(p, st, src, len, lane, valid, dring, sh_rp, sh_pos, &sh_done, PK_BAR_POS, PK_THREADS, PK_BAR_DONE, 96);
+    return;
+  }
+
+  const float bw = p.agc_bw, gmin = p.agc_min, gmax = p.agc_max;
+  const uint32_t d_lane = smem_u32(dring) + ((uint32_t)lane << 2);
+  const uint32_t y_lane = smem_u32(yring) + ((uint32_t)lane << 2);
+  const uint32_t g_lane = smem_u32(gring) + ((uint32_t)lane << 2);
+
+  if (role == R_A) {
+    // ================================================= AGC =================================================
+    uint32_t apos = 0;
+    float ag = 0.0f;
+    ws_bar_arrive(PK_BAR_DONE, 96);
+    while (true) {
+      ws_bar_sync(PK_BAR_POS, PK_THREADS);
+      if (sh_done) break;
+      const uint32_t rq = sh_rq[lane];
+      const uint32_t fpos = sh_pos[lane];
+      const uint32_t rp = sh_frp[lane];  // as of the previous round: the refill running now only adds to it
+      if (rq & 1u) { apos = fpos; ag = sh_g[lane]; }
+      const float bw_eff = (rq & 2u) ? 0.0f : bw;    // (!locked as f32) * (1-|y|) * bw   agc.rs:74
+      int n = min((int)PK_ADV, min((int)(rp - apos), (int)(fpos + PK_LEAD - apos)));
+      n = max(n, 0);
+      const int nmax = __reduce_max_sync(0xffffffffu, n);
+      float g = ag;
+      // 8 samples per step; the d values of the next step are loaded before this step's stores (the explicit
+      // shared-memory accesses keep their program order, so the load latency would otherwise sit on the gain chain)
+      float dn[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dn[j] = lds_f32(d_lane + (((apos + (uint32_t)j) & (WS_DRING - 1)) << 7));
+      for (int k = 0; k < nmax; k += 8) {
+        float dv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dv[j] = dn[j];
+        if (k + 8 < nmax) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dn[j] = lds_f32(d_lane + (((apos + (uint32_t)(k + 8 + j)) & (WS_DRING - 1)) << 7));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool act = (k + j) < n;
+          const float y = FMUL(dv[j], g);                                                 // agc.rs:73
+          g = fminf(fmaxf(FADD(g, FMUL(FSUB(1.0f, fabsf(y)), bw_eff)), gmin), gmax);      // agc.rs:74-75
+          pk_sts_y(y_lane, apos + (uint32_t)(k + j), y, act);                             // demod.rs:177-179
+          pk_sts_pred(g_lane + (((apos + (uint32_t)(k + j)) & (PK_GRING - 1)) << 7), g, act);
+        }
+      }
+      if (n > 0) {
+        apos += (uint32_t)n;
+        ag = lds_f32(g_lane + (((apos - 1u) & (PK_GRING - 1)) << 7));   // the gain after this lane's last sample
+      }
+      sh_apos[lane] = apos;
+      __threadfence_block();
+      ws_bar_arrive(PK_BAR_DONE, 96);
+    }
+    return;
+  }
+
+  if (role == R_S) {
+    // ============================================== space filter ==============================================
+    while (true) {
+      ws_bar_sync(PK_BAR_POS, PK_THREADS);
+      if (sh_done) break;
+      sh_space[lane] = pk_mag(yring, taps.space, lane, sh_pos[lane]);
+      __threadfence_block();
+      ws_bar_arrive(PK_BAR_SPACE, 64);
+    }
+    return;
+  }
+
+  // ================================================= consumer =================================================
+  Lane a;
+  lane_load(a, p, st, s);
+  uint32_t pos = 0;
+  int cfire = fire_clock(a.until, a.clock);
+  uint32_t pend = 0;       // SYM_BYTE_READY | SYM_ADJUSTED while parked (byte-phase alignment, see same_rx_fast_kernel)
+  uint32_t round_ctr = 0;
+  bool la_valid = false;   // the AGC warp's chain continues this lane's exact state under the current lock flag
+
+  while (true) {
+    ws_bar_sync(PK_BAR_DONE, 96);           // refill and AGC of the previous round are complete and visible
+    if (!__any_sync(0xffffffffu, pos < len || pend != 0u)) {
+      if (lane == 0) sh_done = 1u;
+      __threadfence_block();
+      ws_bar_arrive(PK_BAR_POS, PK_THREADS);
+      break;
+    }
+    // ---------------- segment: this lane's samples up to its next TED instant (A2, A3) ----------------
+    const uint32_t rp = sh_rp[lane];
+    const uint32_t apos = sh_apos[lane];
+    int nseg = 0;
+    if (pos < len && pend == 0u) nseg = min(cfire - a.clock, (int)(rp - pos));
+    round_ctr += 1;
+    const bool byte_round = (round_ctr & 15u) == 0u;
+    const uint32_t lock_now = a.flags & FLAG_AGC_LOCKED;
+    const bool use_la = la_valid && (int)(apos - pos) >= nseg;
+    const bool need_fb = nseg > 0 && !use_la;
+    if (__any_sync(0xffffffffu, need_fb)) {
+      // fallback: run the recurrence here (start of a chunk, after a lock flip, AGC warp not far enough)
+      const int nfb = __reduce_max_sync(0xffffffffu, need_fb ? nseg : 0);
+      const float bw_eff = lock_now ? 0.0f : bw;
+      float g = a.g;
+      for (int k = 0; k < nfb; ++k) {
+        const bool act = need_fb && k < nseg;
+        const float dv = lds_f32(d_lane + (((pos + (uint32_t)k) & (WS_DRING - 1)) << 7));
+        const float y = FMUL(dv, g);
+        const float gn = fminf(fmaxf(FADD(g, FMUL(FSUB(1.0f, fabsf(y)), bw_eff)), gmin), gmax);
+        if (act) g = gn;
+        pk_sts_y(y_lane, pos + (uint32_t)k, y, act);
+      }
+      if (need_fb) a.g = g;
+    }
+    if (use_la && nseg > 0) a.g = lds_f32(g_lane + (((pos + (uint32_t)nseg - 1u) & (PK_GRING - 1)) << 7));
+    pos += (uint32_t)nseg;
+    a.clock += nseg;
+    const bool fire = (nseg > 0) && (a.clock == cfire);
+    const bool restart = !la_valid || need_fb;
+    la_valid = true;
+    sh_pos[lane] = pos;
+    sh_g[lane] = a.g;
+    sh_frp[lane] = rp;
+    sh_rq[lane] = (restart ? 1u : 0u) | (lock_now ? 2u : 0u);
+    __threadfence_block();
+    ws_bar_arrive(PK_BAR_POS, PK_THREADS);
+
+    // ---------------- TED instant (A4, A5): mark here, space from warp S ----------------
+    // what the timing loop needs besides the soft symbol is computed first, off the critical path
+    const float rem = FSUB(a.until, (float)a.clock);                         // receiver.rs:352
+    const float off = rclamp(rem, -0.5f, 0.5f);                              // symsync.rs:220
+    const float offq = __fdiv_rn(off, p.spt);                                // symsync.rs:225
+    asm volatile("" ::"f"(offq));
+    const float mag_m = pk_mag(yring, taps.mark, lane, pos);
+    asm volatile("" ::"f"(mag_m));          // keep the mark magnitude ahead of the wait for the space magnitude
+    ws_bar_sync(PK_BAR_SPACE, 64);
+    bool have_sym = false;
+    if (fire) {
+      const float soft = rclamp(FSUB(mag_m, sh_space[lane]), -1.0f, 1.0f);   // demod.rs:163
+      a.clock = 0;
+      have_sym = ted_step(a, p, soft, off, offq);
+      cfire = fire_clock(a.until, 0);
+    }
+    // ---------------- symbol: squelch now (A6), byte path (A7-A9) on the aligned rounds ----------------
+    if (have_sym) pend = symbol_squelch(a, p, s, st, blob, a.ted1, a.ted2, a.n0 + pos);
+    if (byte_round && __any_sync(0xffffffffu, pend != 0u)) {
+      if (pend != 0u) {
+        symbol_byte(a, p, s, st, blob, (pend & SYM_ADJUSTED) != 0u, a.n0 + pos);
+        pend = 0u;
+      }
+    }
+    // a flipped lock flag invalidates what the AGC warp computed from pos on
+    if ((a.flags & FLAG_AGC_LOCKED) != lock_now) la_valid = false;
+  }
+
+  if (!valid || len == 0u) return;
+  lane_store(a, p, st, a.n0 + pos);
+  for (int i = 0; i < FAST_NTAPS; ++i)
+    LANE_ST(st, L, L.win + i) = __float_as_uint(yring[((int)(pos + i - FAST_NTAPS) & (PK_YRING - 1)) * 32 + lane]);
+}
+
 // Constructor state (receiver.rs:502-560) or SameReceiver::reset (receiver.rs:182-198) for the selected streams.
 // `ids` == nullptr: all streams.  `after_reset`: AGC gain 1.0 (agc.rs:61) instead of min(1, min_gain) (agc.rs:55).
 __global__ void same_init_kernel(const __grid_constant__ SameParams p, const uint32_t* __restrict__ ids, uint32_t n,
@@ -860,12 +1142,15 @@ extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps,
                                       const unsigned long long* d_offsets, const uint32_t* d_lengths,
                                       cudaStream_t stream) {
   const uint32_t blocks = (p->n_streams + 31u) / 32u;
-  // force_generic: 0 = auto (warp-specialised fast kernel), 1 = generic kernel, 2 = single-warp fast kernel
+  // force_generic: 0 = auto (warp-specialised fast kernel), 1 = generic kernel, 2 = single-warp fast kernel,
+  //                3 = pipelined four-warp kernel
   if (force_generic != 1 && p->ntaps == FAST_NTAPS && p->dc_len == FAST_DCL) {
     const uint32_t lanes = lanes_per_warp ? lanes_per_warp : 32u;
     const uint32_t fblocks = (p->n_streams + lanes - 1u) / lanes;
     if (force_generic == 2)
       same_dev::same_rx_fast_kernel<<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes);
+    else if (force_generic == 3)
+      same_dev::same_rx_pipe_kernel<<<fblocks, PK_THREADS, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes);
     else
       same_dev::same_rx_ws_kernel<<<fblocks, WS_THREADS, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes);
   } else if (p->ntaps <= 64 && p->dc_len <= 16) {

@@ -302,16 +302,17 @@ __device__ __noinline__ void eq_reset(const SameParams& p, uint32_t s) {
 // A5: one TED instant.  `rem` = until - clock as f32 (receiver.rs:352), `soft` = demodulated sample (demod.rs:163).
 // Returns true when the TED emitted a symbol (zero = ted1, sym = ted2).  Updates `until`.
 // ----------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool ted_step(Lane& a, const SameParams& p, float soft, float rem) {
+// `off` = clamp(rem, -0.5, 0.5) (symsync.rs:220) and `offq` = off / samples-per-TED (symsync.rs:225) do not depend on
+// the soft symbol; callers may compute them ahead of the matched filter.
+__device__ __forceinline__ bool ted_step(Lane& a, const SameParams& p, float soft, float off, float offq) {
   a.ted0 = a.ted1; a.ted1 = a.ted2; a.ted2 = soft;      // symsync.rs:279
   a.tedcnt = (a.tedcnt + 1u) & 1u;                      // symsync.rs:280
-  const float off = rclamp(rem, -0.5f, 0.5f);           // symsync.rs:220
   bool have_sym = false;
   if (a.tedcnt == 1u) {
     const float alpha = (a.flags & FLAG_BW_LOCKED) ? p.alpha_l : p.alpha_u;
     const float beta = (a.flags & FLAG_BW_LOCKED) ? p.beta_l : p.beta_u;
     const float terr = FMUL(a.ted1, FSUB(rsignum(a.ted0), rsignum(a.ted2)));   // symsync.rs:311-316
-    const float e = rclamp(FSUB(terr, __fdiv_rn(off, p.spt)), -1.0f, 1.0f);    // symsync.rs:225
+    const float e = rclamp(FSUB(terr, offq), -1.0f, 1.0f);                     // symsync.rs:225
     a.pavg = rclamp(FADD(a.pavg, FMUL(beta, e)), p.pmin, p.pmax);              // symsync.rs:228-229
     a.pinst = FADD(FADD(a.pavg, FMUL(alpha, e)), off);                         // symsync.rs:233
     if (a.pinst < 0.0f) a.pinst = a.pavg;
@@ -321,6 +322,10 @@ __device__ __forceinline__ bool ted_step(Lane& a, const SameParams& p, float sof
   }
   a.until = a.pinst;                                                           // receiver.rs:382
   return have_sym;
+}
+__device__ __forceinline__ bool ted_step(Lane& a, const SameParams& p, float soft, float rem) {
+  const float off = rclamp(rem, -0.5f, 0.5f);           // symsync.rs:220
+  return ted_step(a, p, soft, off, __fdiv_rn(off, p.spt));
 }
 
 // ----------------------------------------------------------------------------------------------------------------

@@ -222,7 +222,7 @@ def test_device_and_host_submit_agree_and_ragged_lengths():
 
 def test_fast_and_generic_kernels_agree():
     """The 22050 Hz fast kernels (integer DC blocker, packed FFMA2 matched filter, 16-byte loads; warp-specialised
-    producer/consumer and single-warp forms) and the rate-generic kernel (literal f32 recursion) must give identical
+    producer/consumer, five-warp pipelined and single-warp forms) and the rate-generic kernel (literal f32 recursion) must give identical
     events AND identical resident state: chunks alternate between the three kernels mid-stream, with ragged, odd and
     unaligned chunk lengths."""
     _torch()
@@ -237,7 +237,7 @@ def test_fast_and_generic_kernels_agree():
     got = [[] for _ in recs]
     k = 0
     while any(p < len(r) for p, r in zip(pos, recs)):
-        rx.set_option("force_generic", k % 3)   # 0 warp-specialised fast kernel, 1 generic, 2 single-warp fast kernel
+        rx.set_option("force_generic", k % 4)   # 0 warp-specialised, 1 generic, 2 single-warp fast, 3 pipelined
         k += 1
         chunks = []
         for s_ in range(len(recs)):
@@ -251,6 +251,35 @@ def test_fast_and_generic_kernels_agree():
         o = Oracle(oracle_cfg_from(b))
         o.process_s16(recs[s_])
         assert_events_equal(want[s_], o.events(), f"stream {s_} generic kernel vs oracle")
+
+
+@pytest.mark.parametrize("kernel", [0, 2, 3])
+def test_each_fast_kernel_matches_oracle(kernel):
+    """Every fast-kernel flavour on its own, whole streams in one submit and in 3 s chunks: golden recordings and
+    synthetic streams with bursts against the oracle, event for event."""
+    _torch()
+    recs = [load_golden_recording(n) for n in NAMES]
+    recs += [synth.render_numpy(synth.plan_stream(100 + i, seconds=45.0), 45 * 22050) for i in range(6)]
+    b = sb.SameReceiverBuilder.samedec(22050)
+    want = []
+    for r in recs:
+        o = Oracle(oracle_cfg_from(b))
+        o.process_s16(r)
+        want.append(o.events())
+    rx = b.build_batch(len(recs))
+    rx.set_option("force_generic", kernel)
+    got = rx.process(recs)
+    for s_ in range(len(recs)):
+        assert_events_equal(got[s_], want[s_], f"kernel {kernel} stream {s_} one submit")
+    rx = b.build_batch(len(recs))
+    rx.set_option("force_generic", kernel)
+    got = [[] for _ in recs]
+    step = 3 * 22050 + 7
+    for lo in range(0, max(len(r) for r in recs), step):
+        for s_, e in enumerate(rx.process([r[lo:lo + step] for r in recs])):
+            got[s_].extend(e)
+    for s_ in range(len(recs)):
+        assert_events_equal(got[s_], want[s_], f"kernel {kernel} stream {s_} chunked")
 
 
 def test_lane_sparse_warps_give_identical_results():
