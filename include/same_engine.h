@@ -174,8 +174,12 @@ int same_engine_drain_events(same_engine* e, same_event* events, size_t events_c
 int same_engine_enable_soft_trace(same_engine* e, uint32_t cap_per_stream);
 int same_engine_read_soft_trace(same_engine* e, uint32_t stream, same_soft_symbol* out, size_t cap, size_t* n);
 
-/* Engine options.  "force_generic" = 1 runs the rate-generic kernel even where the 22050 Hz fast kernel applies (both
- * must produce identical results; used by the tests to cross-check them).  Implies sync. */
+/* Engine options (diagnostic; every setting must produce identical results, the tests cross-check them).
+ *   "force_generic"   0 engine picks the kernel from the batch size (default); 1 rate-generic kernel even where the
+ *                     22050 Hz fast kernels apply; 2 single-warp fast kernel; 3 four-warp pipelined kernel;
+ *                     4 three-warp kernel
+ *   "lanes_per_warp"  streams per warp of the fast kernels (1, 2, 4, 8, 16, 32)
+ * Implies sync. */
 int same_engine_set_option(same_engine* e, const char* key, int value);
 
 /* Timing of the last completed submit, measured with CUDA events on the engine's stream: host->device copy and

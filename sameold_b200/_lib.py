@@ -109,6 +109,9 @@ def load():
     if _LIB is not None:
         return _LIB
     path = _build.build_native() if _build.needs_build() else _build.LIB
+    alt = os.environ.get("SAME_B200_LIB")   # diagnostic: A/B-time another in-tree build of the same ABI
+    if alt:
+        path = alt
     try:
         lib = C.CDLL(path)
     except OSError as e:  # pragma: no cover

@@ -79,7 +79,7 @@ struct same_engine {
   int force_generic = 0;
   uint32_t lanes_per_warp = 32;   // streams per warp in the fast kernel (lane-sparse warps for small batches)
   int sm_count = 148;
-  int kernel_auto = 0;            // fast-kernel flavour when force_generic == 0: 0 warp-specialised, 2 single-warp
+  int kernel_auto = 0;            // fast-kernel flavour when force_generic == 0: 3 pipelined, 4 three-warp, 2 single-warp
   same_derived derived;
   cudaStream_t compute = nullptr, copy = nullptr;
   uint32_t* d_state = nullptr;
@@ -342,23 +342,27 @@ int same_engine_create(const same_config* cfg_in, int device, uint32_t n_streams
   if (const char* fg = getenv("SAME_FORCE_GENERIC")) e->force_generic = atoi(fg);
   {
     // Kernel / mapping policy for the 22050 Hz class (measured on B200, profiles/README.md):
-    //  * up to 2 blocks per SM: warp-specialised kernel, 32 streams per block.  Each warp has a scheduler to itself,
-    //    the chain is latency-bound, and moving the refill to a second warp shortens every round.
+    //  * up to 1 block per SM: four-warp pipelined kernel (producer / AGC / space filter / consumer), every warp on
+    //    its own scheduler: the per-stream dependent chain is what bounds the run time, so it is cut into stages.
+    //  * up to 4 blocks per SM: three-warp kernel (producer / look-ahead AGC / consumer): fewer instructions in total,
+    //    still latency-hiding across the co-resident blocks.
     //  * larger batches: single-warp fast kernel, 32 streams per warp (issue-bound regime: the fewest instructions win
-    //    and a producer warp per block would only compete for issue slots).
+    //    and helper warps would only compete for issue slots).
+    //  Measured on B200 (20 s streams, ms per launch, pipelined / three-warp / single-warp): 4096 streams 25.9 / 27.6 /
+    //  44.2; 8192: 39.4 / 33.0 / 45.6; 16384: 78.3 / 45.8 / 47.0; 65536: 237 / 179 / 122.
     // SAME_LANES_PER_WARP / option "lanes_per_warp" spread streams over more, lane-sparse warps (diagnostic).
     int sms = 148;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
     e->sm_count = sms;
     e->lanes_per_warp = 32;
     const uint32_t blocks32 = (n_streams + 31u) / 32u;
-    e->kernel_auto = (blocks32 <= 2u * (uint32_t)sms) ? 0 : 2;   // 0 = warp-specialised, 2 = single-warp fast
+    e->kernel_auto = (blocks32 <= (uint32_t)sms) ? 3 : (blocks32 <= 4u * (uint32_t)sms) ? 4 : 2;
     if (const char* lw = getenv("SAME_LANES_PER_WARP")) {
       uint32_t v = (uint32_t)atoi(lw);
       if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) e->lanes_per_warp = v;
     }
     if (const char* kv = getenv("SAME_KERNEL")) {   // diagnostic: ws | 2 (single warp) | pipe
-      e->kernel_auto = atoi(kv) == 2 ? 2 : (strcmp(kv, "pipe") == 0 || atoi(kv) == 3) ? 3 : 0;
+      e->kernel_auto = atoi(kv) == 2 ? 2 : (strcmp(kv, "pipe") == 0 || atoi(kv) == 3) ? 3 : 4;
     }
   }
   p.spt = sps / 2.0f;                                                         // symsync.rs:146

@@ -857,28 +857,14 @@ __global__ void __launch_bounds__(WS_THREADS) same_rx_ws_kernel(const __grid_con
 //   S: sync POS -> space filter at pos -> arrive SPACE            A, P: sync POS -> work -> arrive DONE
 // ----------------------------------------------------------------------------------------------------------------
 #define PK_THREADS 128
-#define PK_YRING 128       // y ring slots; slots 0..40 are mirrored at 128..168 so a 42-tap window never wraps
-#define PK_YMIRROR (FAST_NTAPS - 1)
-#define PK_GRING 64        // gain ring slots
+#define PK_YRING 128       // y ring slots, each mirrored at slot + 128 so that a 42-tap window never wraps (dynamic smem)
+#define PK_GRING 128       // gain ring slots (same indexing as the d and y rings: one running offset serves all three)
+#define PK_DYN_SMEM ((PK_GRING + 2 * PK_YRING) * 32 * 4)   // gain ring, y ring, y mirror: contiguous
 #define PK_LEAD 48         // the AGC warp stays at most this far ahead of the consumer
 #define PK_ADV 32          // ... and advances at most this much per round
 #define PK_BAR_POS 1       // F -> S, A, P     (128 threads)
 #define PK_BAR_DONE 2      // A, P -> F        (96 threads)
 #define PK_BAR_SPACE 3     // S -> F           (64 threads)
-
-__device__ __forceinline__ void pk_sts_y(uint32_t y_lane, uint32_t sample, float v, bool act) {
-  const uint32_t slot = sample & (PK_YRING - 1);
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %2, 0;\n\tsetp.lt.and.u32 q, %3, 41, p;\n\t"
-      "@p st.shared.f32 [%0], %1;\n\t@q st.shared.f32 [%0+16384], %1;\n\t}" ::"r"(y_lane + (slot << 7)),
-      "f"(v), "r"((uint32_t)act), "r"(slot)
-      : "memory");
-}
-__device__ __forceinline__ void pk_sts_pred(uint32_t addr, float v, bool act) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.f32 [%0], %1;\n\t}" ::"r"(addr), "f"(v),
-               "r"((uint32_t)act)
-               : "memory");
-}
 
 // |matched filter output| over the 42 samples that end at sample index `end` (exclusive); taps from the constant bank.
 // One rounded multiply and one rounded add per component and tap, newest sample first (demod.rs:156-163).
@@ -903,9 +889,10 @@ __global__ void __launch_bounds__(PK_THREADS) same_rx_pipe_kernel(const __grid_c
                                                                   const unsigned long long* __restrict__ offsets,
                                                                   const uint32_t* __restrict__ lengths,
                                                                   const uint32_t lanes) {
+  extern __shared__ float pk_dyn[];           // gring[128][32], yring[2 * 128][32]: one address register serves all
+  float* const gring = pk_dyn;
+  float* const yring = pk_dyn + PK_GRING * 32;
   __shared__ float dring[WS_DRING * 32];
-  __shared__ float yring[(PK_YRING + PK_YMIRROR) * 32];
-  __shared__ float gring[PK_GRING * 32];
   __shared__ volatile float sh_space[32];    // |space filter| at pos                  (S)
   __shared__ volatile uint32_t sh_rp[32];    // samples produced per lane              (P)
   __shared__ volatile uint32_t sh_apos[32];  // samples AGC'd per lane                 (A)
@@ -942,7 +929,7 @@ __global__ void __launch_bounds__(PK_THREADS) same_rx_pipe_kernel(const __grid_c
     sh_apos[lane] = 0u;
     for (int i = 0; i < PK_YRING - FAST_NTAPS; ++i) yring[i * 32 + lane] = 0.0f;   // keep never-written slots finite
   } else if (role == R_S) {
-    for (int i = 0; i < PK_YMIRROR; ++i) yring[(PK_YRING + i) * 32 + lane] = 0.0f;
+    for (int i = 0; i < PK_YRING; ++i) yring[(PK_YRING + i) * 32 + lane] = 0.0f;
     sh_space[lane] = 0.0f;
   } else {
     sh_rp[lane] = 0u;
@@ -956,7 +943,6 @@ __global__ void __launch_bounds__(PK_THREADS) same_rx_pipe_kernel(const __grid_c
 
   const float bw = p.agc_bw, gmin = p.agc_min, gmax = p.agc_max;
   const uint32_t d_lane = smem_u32(dring) + ((uint32_t)lane << 2);
-  const uint32_t y_lane = smem_u32(yring) + ((uint32_t)lane << 2);
   const uint32_t g_lane = smem_u32(gring) + ((uint32_t)lane << 2);
 
   if (role == R_A) {
@@ -976,31 +962,30 @@ __global__ void __launch_bounds__(PK_THREADS) same_rx_pipe_kernel(const __grid_c
       n = max(n, 0);
       const int nmax = __reduce_max_sync(0xffffffffu, n);
       float g = ag;
-      // 8 samples per step; the d values of the next step are loaded before this step's stores (the explicit
-      // shared-memory accesses keep their program order, so the load latency would otherwise sit on the gain chain)
-      float dn[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dn[j] = lds_f32(d_lane + (((apos + (uint32_t)j) & (WS_DRING - 1)) << 7));
+      // 8 samples per step, the d values of the next step prefetched.  One running byte offset (ring slot * 128 +
+      // lane * 4) addresses all three rings.  Every lane stores all nmax (rounded up to 8) samples: what lies beyond
+      // its own n is overwritten with the right values before anything reads it, and lands at most 79 samples ahead
+      // of the consumer, which aliases nothing live in 128-slot rings (the demod window reaches back 42 samples).
+      // Software pipeline, distance 2: the d value of sample j+2 is loaded right after the stores of sample j-1.
+      // The explicit shared-memory accesses keep their program order, so the stores have to issue in the shadow of
+      // the gain chain (one dependent op every 4-5 cycles) instead of in a bunch after it.
+      uint32_t o0 = (apos & (WS_DRING - 1)) << 7, o1 = (o0 + 128u) & 0x3f80u;
+      float d0 = lds_f32(d_lane + o0), d1 = lds_f32(d_lane + o1);
       for (int k = 0; k < nmax; k += 8) {
-        float dv[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dv[j] = dn[j];
-        if (k + 8 < nmax) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dn[j] = lds_f32(d_lane + (((apos + (uint32_t)(k + 8 + j)) & (WS_DRING - 1)) << 7));
-        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const bool act = (k + j) < n;
-          const float y = FMUL(dv[j], g);                                                 // agc.rs:73
+          const uint32_t o2 = (o1 + 128u) & 0x3f80u;
+          const float d2 = lds_f32(d_lane + o2);
+          const float y = FMUL(d0, g);                                                    // agc.rs:73
           g = fminf(fmaxf(FADD(g, FMUL(FSUB(1.0f, fabsf(y)), bw_eff)), gmin), gmax);      // agc.rs:74-75
-          pk_sts_y(y_lane, apos + (uint32_t)(k + j), y, act);                             // demod.rs:177-179
-          pk_sts_pred(g_lane + (((apos + (uint32_t)(k + j)) & (PK_GRING - 1)) << 7), g, act);
+          asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.f32 [%0+16384], %2;\n\tst.shared.f32 [%0+32768], %2;"
+                       ::"r"(g_lane + o0), "f"(g), "f"(y) : "memory");                     // gain | y | y mirror
+          o0 = o1; o1 = o2; d0 = d1; d1 = d2;
         }
       }
       if (n > 0) {
         apos += (uint32_t)n;
-        ag = lds_f32(g_lane + (((apos - 1u) & (PK_GRING - 1)) << 7));   // the gain after this lane's last sample
+        ag = gring[((apos - 1u) & (PK_GRING - 1)) * 32 + lane];         // the gain after this lane's last sample
       }
       sh_apos[lane] = apos;
       __threadfence_block();
@@ -1058,8 +1043,12 @@ __global__ void __launch_bounds__(PK_THREADS) same_rx_pipe_kernel(const __grid_c
         const float dv = lds_f32(d_lane + (((pos + (uint32_t)k) & (WS_DRING - 1)) << 7));
         const float y = FMUL(dv, g);
         const float gn = fminf(fmaxf(FADD(g, FMUL(FSUB(1.0f, fabsf(y)), bw_eff)), gmin), gmax);
-        if (act) g = gn;
-        pk_sts_y(y_lane, pos + (uint32_t)k, y, act);
+        if (act) {
+          g = gn;
+          const uint32_t slot = (pos + (uint32_t)k) & (PK_YRING - 1);
+          yring[slot * 32 + lane] = y;
+          yring[(slot + PK_YRING) * 32 + lane] = y;
+        }
       }
       if (need_fb) a.g = g;
     }
@@ -1142,15 +1131,22 @@ extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps,
                                       const unsigned long long* d_offsets, const uint32_t* d_lengths,
                                       cudaStream_t stream) {
   const uint32_t blocks = (p->n_streams + 31u) / 32u;
-  // force_generic: 0 = auto (warp-specialised fast kernel), 1 = generic kernel, 2 = single-warp fast kernel,
-  //                3 = pipelined four-warp kernel
+  // force_generic: 1 = generic kernel, 2 = single-warp fast kernel, 3 = pipelined four-warp kernel,
+  //                4 (or 0) = three-warp kernel.  The fast kernels need the 22050 Hz geometry (42 taps, DC length 16).
   if (force_generic != 1 && p->ntaps == FAST_NTAPS && p->dc_len == FAST_DCL) {
     const uint32_t lanes = lanes_per_warp ? lanes_per_warp : 32u;
     const uint32_t fblocks = (p->n_streams + lanes - 1u) / lanes;
     if (force_generic == 2)
       same_dev::same_rx_fast_kernel<<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes);
     else if (force_generic == 3)
-      same_dev::same_rx_pipe_kernel<<<fblocks, PK_THREADS, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes);
+{
+      // per device, cheap: set on every launch rather than tracking which devices have seen it
+      cudaError_t e = cudaFuncSetAttribute(same_dev::same_rx_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           PK_DYN_SMEM);
+      if (e != cudaSuccess) return e;
+      same_dev::same_rx_pipe_kernel<<<fblocks, PK_THREADS, PK_DYN_SMEM, stream>>>(*p, *taps2, d_samples, d_offsets,
+                                                                                   d_lengths, lanes);
+    }
     else
       same_dev::same_rx_ws_kernel<<<fblocks, WS_THREADS, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes);
   } else if (p->ntaps <= 64 && p->dc_len <= 16) {
