@@ -44,8 +44,8 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=4096, help="streams per GPU (config 3: 4096)")
     ap.add_argument("--seconds", type=float, default=60.0, help="stream duration")
-    ap.add_argument("--e2e-chunks", type=int, default=6, help="time-chunks per step on the host-buffer path")
-    ap.add_argument("--cpu-sample-streams", type=int, default=512)
+    ap.add_argument("--e2e-chunks", type=int, default=24, help="time-chunks per step on the host-buffer path")
+    ap.add_argument("--cpu-sample-streams", type=int, default=1024)
     ap.add_argument("--no-bursts", action="store_true", help="diagnostic: noise-only corpus (not a valid bench line)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

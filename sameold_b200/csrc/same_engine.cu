@@ -88,6 +88,8 @@ struct same_engine {
   uint8_t* d_payload = nullptr;
   unsigned int* d_counters = nullptr;
   unsigned int* h_counters = nullptr;   // pinned
+  uint8_t* h_stage = nullptr;           // pinned staging for event / payload read-back (STAGE_BYTES, used as two halves)
+  cudaEvent_t stage_done[2] = {nullptr, nullptr};
   same_soft_symbol* d_trace = nullptr;
   uint32_t* d_ids = nullptr; size_t ids_cap = 0;
   InputBuf in[2];
@@ -130,6 +132,8 @@ int alloc_arenas(same_engine* e, size_t max_events, size_t max_payload) {
   return SAME_OK;
 }
 
+static const size_t STAGE_BYTES = 2 * 48 * 32768;   // two halves of 32768 events (1.5 MiB each)
+
 // Pull the events produced since the last collect from the device arenas into the host pending lists.
 int collect(same_engine* e) {
   CK(e, cudaMemcpyAsync(e->h_counters, e->d_counters, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, e->compute));
@@ -149,14 +153,34 @@ int collect(same_engine* e) {
   }
   const size_t cev = std::min(nev, e->events_cap), cpay = std::min(npay, e->payload_cap);
   if (cev) {
+    // device -> pinned staging (two halves, so the copy of one slice overlaps the append of the other) -> pending lists
     const size_t base_ev = e->pend_events.size(), base_pay = e->pend_payload.size();
-    e->pend_events.resize(base_ev + cev);
-    e->pend_payload.resize(base_pay + cpay);
-    CK(e, cudaMemcpyAsync(e->pend_events.data() + base_ev, e->d_events, cev * sizeof(same_event),
-                          cudaMemcpyDeviceToHost, e->compute));
-    if (cpay)
-      CK(e, cudaMemcpyAsync(e->pend_payload.data() + base_pay, e->d_payload, cpay, cudaMemcpyDeviceToHost, e->compute));
-    CK(e, cudaStreamSynchronize(e->compute));
+    e->pend_events.reserve(base_ev + cev);
+    e->pend_payload.reserve(base_pay + cpay);
+    const size_t half = STAGE_BYTES / 2;
+    const uint8_t* src[2] = {reinterpret_cast<const uint8_t*>(e->d_events), e->d_payload};
+    const size_t bytes[2] = {cev * sizeof(same_event), cpay};
+    for (int part = 0; part < 2; ++part) {
+      size_t done = 0, queued = 0, qn[2] = {0, 0};
+      int qslot = 0, pslot = 0, inflight = 0;
+      while (done < bytes[part]) {
+        while (inflight < 2 && queued < bytes[part]) {   // keep both halves in flight
+          const size_t n = std::min(half, bytes[part] - queued);
+          CK(e, cudaMemcpyAsync(e->h_stage + qslot * half, src[part] + queued, n, cudaMemcpyDeviceToHost, e->compute));
+          CK(e, cudaEventRecord(e->stage_done[qslot], e->compute));
+          qn[qslot] = n; queued += n; qslot ^= 1; ++inflight;
+        }
+        CK(e, cudaEventSynchronize(e->stage_done[pslot]));
+        const uint8_t* h = e->h_stage + pslot * half;
+        if (part == 0) {
+          const same_event* ev = reinterpret_cast<const same_event*>(h);
+          e->pend_events.insert(e->pend_events.end(), ev, ev + qn[pslot] / sizeof(same_event));
+        } else {
+          e->pend_payload.insert(e->pend_payload.end(), h, h + qn[pslot]);
+        }
+        done += qn[pslot]; pslot ^= 1; --inflight;
+      }
+    }
     for (size_t i = base_ev; i < base_ev + cev; ++i) e->pend_events[i].data_offset += (uint32_t)base_pay;
   }
   CK(e, cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(unsigned int), e->compute));
@@ -422,6 +446,8 @@ int same_engine_create(const same_config* cfg_in, int device, uint32_t n_streams
   CKC(cudaMalloc(&e->d_counters, 4 * sizeof(unsigned int)));
   CKC(cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(unsigned int), e->compute));
   CKC(cudaHostAlloc(&e->h_counters, 4 * sizeof(unsigned int), cudaHostAllocDefault));
+  CKC(cudaHostAlloc(&e->h_stage, STAGE_BYTES, cudaHostAllocDefault));
+  for (auto& ev : e->stage_done) CKC(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto& b : e->in) {
     CKC(cudaMalloc(&b.d_off, (size_t)n_streams * sizeof(unsigned long long)));
     CKC(cudaMalloc(&b.d_len, (size_t)n_streams * sizeof(uint32_t)));
@@ -463,6 +489,8 @@ void same_engine_destroy(same_engine* e) {
   if (e->d_payload) cudaFree(e->d_payload);
   if (e->d_counters) cudaFree(e->d_counters);
   if (e->h_counters) cudaFreeHost(e->h_counters);
+  if (e->h_stage) cudaFreeHost(e->h_stage);
+  for (auto& ev : e->stage_done) if (ev) cudaEventDestroy(ev);
   if (e->d_trace) cudaFree(e->d_trace);
   if (e->d_ids) cudaFree(e->d_ids);
   for (cudaEvent_t ev : {e->t_h2d0, e->t_h2d1, e->t_k0, e->t_k1, e->t_sw0, e->t_sw1}) if (ev) cudaEventDestroy(ev);
