@@ -398,8 +398,8 @@ class SameBatchReceiver:
         nev, npay = C.c_size_t(), C.c_size_t()
         self._ck(self._lib.same_engine_pending(self._h, C.byref(nev), C.byref(npay)))
         self._keep = None
-        evs = np.zeros(nev.value, self.EVENT_DTYPE)
-        pay = np.zeros(max(npay.value, 1), np.uint8)
+        evs = np.empty(nev.value, self.EVENT_DTYPE)
+        pay = np.empty(max(npay.value, 1), np.uint8)
         if nev.value:
             self._ck(self._lib.same_engine_drain_events(self._h, evs.ctypes.data, nev.value, C.byref(nev), pay.ctypes.data,
                                                         pay.size, C.byref(npay)))
