@@ -111,6 +111,30 @@ def cpu_baseline(host_samples, cfg, cores):
     return audio / best, best, int(nb.sum()), int(nm.sum())
 
 
+def bind_to_gpu_numa_node(device):
+    """Pin this process (and therefore its first-touch host allocations, the pinned sample buffer above all) to the CPU
+    cores of the NUMA node the GPU hangs off, so that with one rank per GPU the host->device copies of different
+    ranks do not cross the socket interconnect.  Best effort; returns the node or None."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(device)
+        bus = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -132,6 +156,7 @@ def main():
     from sameold_b200 import synth, _lib
 
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -265,7 +290,8 @@ def main():
         e2e = {"value": round(audio_per_step * args.steps * world / (e2e_ms * 1e-3), 1), "unit": UNIT,
                "h2d_bytes_per_step": int(ns * n_samples * 2 + nchunk * ns * 12) * world,
                "d2h_bytes_per_step": int(sum_over_ranks(statistics.mean(d2h_bytes))), "ms_per_step": round(e2e_ms / args.steps, 3),
-               "chunks_per_step": nchunk, "api": "same_engine_submit_s16_2d + sync + drain_events (pinned host buffer)"}
+               "chunks_per_step": nchunk, "api": "same_engine_submit_s16_2d + sync + drain_events (pinned host buffer)",
+               "rank0_numa_node": numa_node}
 
     # ---- CPU baseline on rank 0 at N=1 ----
     cpu = None
