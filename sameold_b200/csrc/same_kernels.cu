@@ -852,9 +852,11 @@ __global__ void __launch_bounds__(WS_THREADS) same_rx_ws_kernel(const __grid_con
 // The AGC depends on the consumer only through the lock flag (agc.rs:74), so it runs ahead speculatively and exactly:
 // whenever the consumer's flag flips, or the AGC warp has not got far enough, the consumer runs the recurrence itself
 // with the same arithmetic (fallback below) and tells the AGC warp to restart from its position and gain.
-// Lockstep rounds on three named barriers:
-//   F: sync DONE -> segment -> publish (pos, gain, flag, restart) -> arrive POS -> mark -> sync SPACE -> TED, symbol
-//   S: sync POS -> space filter at pos -> arrive SPACE            A, P: sync POS -> work -> arrive DONE
+// Lockstep rounds on four named barriers:
+//   F: sync DONE -> segment -> publish pos -> arrive POS -> publish (gain, flag, restart) -> arrive AGC -> mark
+//      -> sync SPACE -> TED, symbol
+//   S: sync POS -> space filter at pos -> arrive SPACE     P: sync POS -> refill -> arrive DONE
+//   A: sync AGC -> recurrence -> arrive DONE
 // ----------------------------------------------------------------------------------------------------------------
 #define PK_THREADS 128
 #define PK_YRING 128       // y ring slots, each mirrored at slot + 128 so that a 42-tap window never wraps (dynamic smem)
@@ -862,9 +864,10 @@ __global__ void __launch_bounds__(WS_THREADS) same_rx_ws_kernel(const __grid_con
 #define PK_DYN_SMEM ((PK_GRING + 2 * PK_YRING) * 32 * 4)   // gain ring, y ring, y mirror: contiguous
 #define PK_LEAD 48         // the AGC warp stays at most this far ahead of the consumer
 #define PK_ADV 32          // ... and advances at most this much per round
-#define PK_BAR_POS 1       // F -> S, A, P     (128 threads)
+#define PK_BAR_POS 1       // F -> S, P        (96 threads)   position published
 #define PK_BAR_DONE 2      // A, P -> F        (96 threads)
 #define PK_BAR_SPACE 3     // S -> F           (64 threads)
+#define PK_BAR_AGC 4       // F -> A           (64 threads)   gain / flag / restart published
 
 // |matched filter output| over the 42 samples that end at sample index `end` (exclusive); taps from the constant bank.
 // One rounded multiply and one rounded add per component and tap, newest sample first (demod.rs:156-163).
@@ -937,7 +940,7 @@ __global__ void __launch_bounds__(PK_THREADS) same_rx_pipe_kernel(const __grid_c
   __syncthreads();
 
   if (role == R_P) {
-    ws_producer(p, st, src, len, lane, valid, dring, sh_rp, sh_pos, &sh_done, PK_BAR_POS, PK_THREADS, PK_BAR_DONE, 96);
+    ws_producer(p, st, src, len, lane, valid, dring, sh_rp, sh_pos, &sh_done, PK_BAR_POS, 96, PK_BAR_DONE, 96);
     return;
   }
 
@@ -951,7 +954,7 @@ __global__ void __launch_bounds__(PK_THREADS) same_rx_pipe_kernel(const __grid_c
     float ag = 0.0f;
     ws_bar_arrive(PK_BAR_DONE, 96);
     while (true) {
-      ws_bar_sync(PK_BAR_POS, PK_THREADS);
+      ws_bar_sync(PK_BAR_AGC, 64);
       if (sh_done) break;
       const uint32_t rq = sh_rq[lane];
       const uint32_t fpos = sh_pos[lane];
@@ -997,7 +1000,7 @@ __global__ void __launch_bounds__(PK_THREADS) same_rx_pipe_kernel(const __grid_c
   if (role == R_S) {
     // ============================================== space filter ==============================================
     while (true) {
-      ws_bar_sync(PK_BAR_POS, PK_THREADS);
+      ws_bar_sync(PK_BAR_POS, 96);
       if (sh_done) break;
       sh_space[lane] = pk_mag(yring, taps.space, lane, sh_pos[lane]);
       __threadfence_block();
@@ -1020,7 +1023,8 @@ __global__ void __launch_bounds__(PK_THREADS) same_rx_pipe_kernel(const __grid_c
     if (!__any_sync(0xffffffffu, pos < len || pend != 0u)) {
       if (lane == 0) sh_done = 1u;
       __threadfence_block();
-      ws_bar_arrive(PK_BAR_POS, PK_THREADS);
+      ws_bar_arrive(PK_BAR_POS, 96);
+      ws_bar_arrive(PK_BAR_AGC, 64);
       break;
     }
     // ---------------- segment: this lane's samples up to its next TED instant (A2, A3) ----------------
@@ -1052,18 +1056,21 @@ __global__ void __launch_bounds__(PK_THREADS) same_rx_pipe_kernel(const __grid_c
       }
       if (need_fb) a.g = g;
     }
+    // the position first: it is all the space-filter and producer warps wait for
+    sh_pos[lane] = pos + (uint32_t)nseg;
+    __threadfence_block();
+    ws_bar_arrive(PK_BAR_POS, 96);
     if (use_la && nseg > 0) a.g = lds_f32(g_lane + (((pos + (uint32_t)nseg - 1u) & (PK_GRING - 1)) << 7));
     pos += (uint32_t)nseg;
     a.clock += nseg;
     const bool fire = (nseg > 0) && (a.clock == cfire);
     const bool restart = !la_valid || need_fb;
     la_valid = true;
-    sh_pos[lane] = pos;
     sh_g[lane] = a.g;
     sh_frp[lane] = rp;
     sh_rq[lane] = (restart ? 1u : 0u) | (lock_now ? 2u : 0u);
     __threadfence_block();
-    ws_bar_arrive(PK_BAR_POS, PK_THREADS);
+    ws_bar_arrive(PK_BAR_AGC, 64);
 
     // ---------------- TED instant (A4, A5): mark here, space from warp S ----------------
     // what the timing loop needs besides the soft symbol is computed first, off the critical path

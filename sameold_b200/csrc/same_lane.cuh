@@ -251,12 +251,64 @@ __device__ __forceinline__ uint32_t eq_byte_impl(const SameParams& p, uint32_t s
   }
   uint32_t byte = 0;
   if (EXACT) {
+    // Same arithmetic as eq_symbol x 8 (equalize.rs:173-186, LSb first), regrouped for instruction-level parallelism:
+    // the NLMS step sizes relax / (regul + |window|^2) of all eight symbols depend only on the 16 input samples and on
+    // the *squares* of the decisions (always 1.0: a decision is +-1), so they are computed up front, 16 independent
+    // chains; only filter -> decision -> error -> tap update remains sequential.
+    float X[NFF + 16], X2[NFF + 16];     // feed-forward samples: window (oldest first) then the 16 new ones
+    float Y[NFB + 16], Y2[NFB + 16];     // feedback samples: window then (decision, 0) per symbol
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {  // equalize.rs:173-186, LSb first
-      bool bit;
-      eq_symbol<NFF, NFB>(p, q, nff, nfb, S[2 * b], S[2 * b + 1], flags, train_sa, train_cnt, bit);
-      byte |= (bit ? 1u : 0u) << b;
+    for (int i = 0; i < NFF; ++i) X[i] = q.ffw[i];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) X[NFF + k] = S[k];
+#pragma unroll
+    for (int k = 0; k < NFF + 16; ++k) X2[k] = FMUL(X[k], X[k]);
+#pragma unroll
+    for (int i = 0; i < NFB; ++i) { Y[i] = q.fbw[i]; Y2[i] = FMUL(Y[i], Y[i]); }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) Y2[NFB + k] = (k & 1) ? 0.0f : 1.0f;
+    float gff[8], gfb[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      float ss = 0.0f;   // window after pushing (z, s) of symbol b: X[2b+2 .. 2b+1+NFF]   equalize.rs:253, 376-386
+#pragma unroll
+      for (int i = 0; i < NFF; ++i) ss = FADD(ss, X2[2 * b + 2 + i]);
+      gff[b] = __fdiv_rn(p.eq_relax, FADD(p.eq_regul, ss));
+      float st2 = 0.0f;  // feedback window before this symbol's decision is pushed: Y[2b .. 2b+NFB-1]
+#pragma unroll
+      for (int i = 0; i < NFB; ++i) st2 = FADD(st2, Y2[2 * b + i]);
+      gfb[b] = __fdiv_rn(p.eq_relax, FADD(p.eq_regul, st2));
     }
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      float ff = 0.0f, fb = 0.0f;        // newest sample pairs with coeff[0]  filter.rs:363-377
+#pragma unroll
+      for (int i = 0; i < NFF; ++i) ff = FADD(ff, FMUL(X[2 * b + 1 + NFF - i], q.ffc[i]));
+#pragma unroll
+      for (int i = 0; i < NFB; ++i) fb = FADD(fb, FMUL(Y[2 * b + NFB - 1 - i], q.fbc[i]));
+      const float sym_val = FSUB(ff, fb);
+      const bool training = (flags & FLAG_EQ_TRAINING) != 0u;                  // equalize.rs:277-300
+      const float est_tr = FSUB(FMUL(2.0f, (float)(train_sa & 1u)), 1.0f);
+      const float sym_est = training ? est_tr : rsignum(sym_val);              // equalize.rs:264-276
+      if (training) {
+        train_sa >>= 1;
+        train_cnt += 1;
+        if (train_cnt >= 32u) flags &= ~FLAG_EQ_TRAINING;
+      }
+      const float err = FSUB(sym_est, sym_val);
+      const float ge_ff = FMUL(gff[b], err), ge_fb = FMUL(gfb[b], -err);       // equalize.rs:315-332, 354-386
+#pragma unroll
+      for (int i = 0; i < NFF; ++i) q.ffc[i] = FADD(q.ffc[i], FMUL(ge_ff, X[2 * b + 1 + NFF - i]));
+#pragma unroll
+      for (int i = 0; i < NFB; ++i) q.fbc[i] = FADD(q.fbc[i], FMUL(ge_fb, Y[2 * b + NFB - 1 - i]));
+      Y[NFB + 2 * b] = sym_est;                                                // equalize.rs:304
+      Y[NFB + 2 * b + 1] = 0.0f;
+      byte |= (sym_est >= 0.0f ? 1u : 0u) << b;
+    }
+#pragma unroll
+    for (int i = 0; i < NFF; ++i) q.ffw[i] = X[16 + i];
+#pragma unroll
+    for (int i = 0; i < NFB; ++i) q.fbw[i] = Y[16 + i];
   } else {
 #pragma unroll 1
     for (int b = 0; b < 8; ++b) {
