@@ -259,6 +259,11 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
   // index is a multiple of 16, where all parked lanes run the equalizer/framer together.  Bytes are 16 TED instants
   // apart, so after its first wait a lane's bytes keep falling on those rounds: the warp pays for the byte path once
   // per 16 rounds instead of once per in-burst lane.
+  // TED-phase alignment: the timing loop emits a symbol at every second TED instant (symsync.rs:280).  A lane whose
+  // instant counter is out of step with the round counter sits out one round, after which all lanes of the warp emit
+  // their symbols on the even rounds: the symbol-rate stages (loop filter, squelch, link bookkeeping) then run every
+  // second round for the whole warp instead of every round for half of its lanes.  Byte rounds are even rounds, so
+  // byte parking (an even number of rounds) keeps the phase.  Neither kind of parking changes what a lane computes.
   uint32_t pend = 0;       // SYM_BYTE_READY | SYM_ADJUSTED while parked
   uint32_t round_ctr = 0;
 
@@ -371,6 +376,7 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
     // o = ((pos + k) & 63) * 128 + lane * 4 relative to each ring.
     int nseg = 0;
     if (pos < len && pend == 0u) nseg = min(cfire - a.clock, (int)(rp - pos));
+    if (((a.tedcnt ^ round_ctr) & 1u) != 0u) nseg = 0;   // TED-phase alignment, see below
     const int maxseg = __reduce_max_sync(0xffffffffu, nseg);
     const int nmin = __reduce_min_sync(0xffffffffu, nseg);
     const float bw_eff = (a.flags & FLAG_AGC_LOCKED) ? 0.0f : bw;   // (!locked as f32) * (1-|y|) * bw   agc.rs:74
@@ -738,10 +744,11 @@ __global__ void __launch_bounds__(WS_THREADS) same_rx_ws_kernel(const __grid_con
     // ---------------- segment: AGC over this lane's samples up to its next TED instant (A2, A3) ----------------
     const uint32_t rp = sh_rp[lane];
     int nseg = 0;
-    if (pos < len && pend == 0u) nseg = min(cfire - a.clock, (int)(rp - pos));
-    const int maxseg = __reduce_max_sync(0xffffffffu, nseg);
     round_ctr += 1;
     const bool byte_round = (round_ctr & 15u) == 0u;
+    if (pos < len && pend == 0u) nseg = min(cfire - a.clock, (int)(rp - pos));
+    if (((a.tedcnt ^ round_ctr) & 1u) != 0u) nseg = 0;   // TED-phase alignment (see same_rx_fast_kernel)
+    const int maxseg = __reduce_max_sync(0xffffffffu, nseg);
     const int nmin = __reduce_min_sync(0xffffffffu, nseg);
     const float bw_eff = (a.flags & FLAG_AGC_LOCKED) ? 0.0f : bw;   // (!locked as f32) * (1-|y|) * bw   agc.rs:74
     // use the look-ahead only if every lane that works this round has one (uniform start index keeps the loop simple)
@@ -1031,9 +1038,10 @@ __global__ void __launch_bounds__(PK_THREADS) same_rx_pipe_kernel(const __grid_c
     const uint32_t rp = sh_rp[lane];
     const uint32_t apos = sh_apos[lane];
     int nseg = 0;
-    if (pos < len && pend == 0u) nseg = min(cfire - a.clock, (int)(rp - pos));
     round_ctr += 1;
     const bool byte_round = (round_ctr & 15u) == 0u;
+    if (pos < len && pend == 0u) nseg = min(cfire - a.clock, (int)(rp - pos));
+    if (((a.tedcnt ^ round_ctr) & 1u) != 0u) nseg = 0;   // TED-phase alignment (see same_rx_fast_kernel)
     const uint32_t lock_now = a.flags & FLAG_AGC_LOCKED;
     const bool use_la = la_valid && (int)(apos - pos) >= nseg;
     const bool need_fb = nseg > 0 && !use_la;
