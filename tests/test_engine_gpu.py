@@ -324,6 +324,30 @@ def test_large_batches_engine_policy_matches_generic_kernel(ns):
         assert_events_equal(by_stream[s_], o.events(), f"stream {s_} of {ns}")
 
 
+def test_long_single_stream_in_time_chunks():
+    """Config 5 shape (one continuous stream, sparse bursts), shortened to 16 minutes: clusters of SAME bursts separated
+    by minutes of noise, fed in 60 s chunks to a one-stream engine; events and messages must equal the oracle's."""
+    _torch()
+    rng = np.random.default_rng(5)
+    parts = []
+    for i in range(4):
+        parts.append(synth.render_numpy(synth.plan_stream(300 + i, seconds=60.0), 60 * 22050))
+        parts.append(np.clip(np.rint(rng.normal(0.0, 3663.0, 180 * 22050)), -32768, 32767).astype(np.int16))
+    stream = np.concatenate(parts)
+    b = sb.SameReceiverBuilder.samedec(22050)
+    o = Oracle(oracle_cfg_from(b))
+    o.process_s16(stream)
+    want = o.events()
+    assert sum(1 for e in want if e.is_message) >= 4
+    rx = b.build_batch(1)
+    got = []
+    step = 60 * 22050
+    for lo in range(0, len(stream), step):
+        got.extend(rx.process([stream[lo:lo + step]])[0])
+    assert_events_equal(got, want, "16-minute stream in 60 s chunks")
+    assert rx.input_sample_counters()[0] == len(stream)
+
+
 def test_lane_sparse_warps_give_identical_results():
     """Small batches run with fewer streams per warp (latency-bound regime); the mapping must not change results."""
     _torch()
