@@ -372,8 +372,8 @@ int same_engine_create(const same_config* cfg_in, int device, uint32_t n_streams
     //    still latency-hiding across the co-resident blocks.
     //  * larger batches: single-warp fast kernel, 32 streams per warp (issue-bound regime: the fewest instructions win
     //    and helper warps would only compete for issue slots).
-    //  Measured on B200 (20 s streams, ms per launch, pipelined / three-warp / single-warp): 4096 streams 25.9 / 27.6 /
-    //  44.2; 8192: 39.4 / 33.0 / 45.6; 16384: 78.3 / 45.8 / 47.0; 65536: 237 / 179 / 122.
+    //  Measured on B200 (20 s streams, ms per launch, pipelined / three-warp / single-warp): 4096 streams 24.0 / 24.9 /
+    //  41.6; 8192: 36.8 / 29.1 / 42.4; 16384: 74.6 / 40.0 / 43.3; 65536: 228 / 158 / 116  (tools/matrix.sh).
     // SAME_LANES_PER_WARP / option "lanes_per_warp" spread streams over more, lane-sparse warps (diagnostic).
     int sms = 148;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;

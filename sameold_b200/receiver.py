@@ -392,18 +392,26 @@ class SameBatchReceiver:
                             ("kind", "<u4"), ("err", "<u4"), ("data_offset", "<u4"), ("data_len", "<u4"),
                             ("parity_errors", "<u2"), ("voting_bytes", "<u2"), ("flags", "<u4")])
 
-    def drain_raw(self):
+    def drain_raw(self, reuse: bool = False):
         """All pending events as a numpy structured array (same_event records, sorted by stream then occurrence) plus
-        the payload arena — no per-event Python objects (what a high-rate consumer uses)."""
+        the payload arena — no per-event Python objects (what a high-rate consumer uses).  `reuse=True` returns views
+        into buffers owned by the receiver (valid until the next drain): no allocation, no page faults per call."""
         nev, npay = C.c_size_t(), C.c_size_t()
         self._ck(self._lib.same_engine_pending(self._h, C.byref(nev), C.byref(npay)))
         self._keep = None
-        evs = np.empty(nev.value, self.EVENT_DTYPE)
-        pay = np.empty(max(npay.value, 1), np.uint8)
+        if reuse:
+            if getattr(self, "_raw_ev", None) is None or self._raw_ev.size < nev.value:
+                self._raw_ev = np.empty(max(nev.value, 1) * 5 // 4 + 1024, self.EVENT_DTYPE)
+            if getattr(self, "_raw_pay", None) is None or self._raw_pay.size < npay.value:
+                self._raw_pay = np.empty(max(npay.value, 1) * 5 // 4 + 4096, np.uint8)
+            evs, pay = self._raw_ev, self._raw_pay
+        else:
+            evs = np.empty(nev.value, self.EVENT_DTYPE)
+            pay = np.empty(max(npay.value, 1), np.uint8)
         if nev.value:
-            self._ck(self._lib.same_engine_drain_events(self._h, evs.ctypes.data, nev.value, C.byref(nev), pay.ctypes.data,
+            self._ck(self._lib.same_engine_drain_events(self._h, evs.ctypes.data, evs.size, C.byref(nev), pay.ctypes.data,
                                                         pay.size, C.byref(npay)))
-        return evs, pay[: npay.value]
+        return evs[: nev.value], pay[: npay.value]
 
     def drain_by_stream(self) -> List[List[SameReceiverEvent]]:
         out: List[List[SameReceiverEvent]] = [[] for _ in range(self.n_streams)]
