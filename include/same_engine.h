@@ -179,6 +179,8 @@ int same_engine_read_soft_trace(same_engine* e, uint32_t stream, same_soft_symbo
  *                     22050 Hz fast kernels apply; 2 single-warp fast kernel; 3 four-warp pipelined kernel;
  *                     4 three-warp kernel
  *   "lanes_per_warp"  streams per warp of the fast kernels (1, 2, 4, 8, 16, 32)
+ *   "device_sort"     1 (default): big batches of events are put into per-stream order on the device before the
+ *                     read-back; 0: always on the host
  * Implies sync. */
 int same_engine_set_option(same_engine* e, const char* key, int value);
 

@@ -20,6 +20,9 @@ extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps,
                                       uint32_t lanes_per_warp, const int16_t* d_samples,
                                       const unsigned long long* d_offsets, const uint32_t* d_lengths,
                                       cudaStream_t stream);
+extern "C" cudaError_t same_launch_evsort(const same_event* d_events, uint32_t n, uint32_t n_streams, uint32_t* d_cnt,
+                                          uint32_t* d_minseq, uint32_t* d_start, same_event* d_sorted, uint32_t* d_bad,
+                                          cudaStream_t stream);
 extern "C" cudaError_t same_launch_init(const SameParams* p, const uint32_t* d_ids, uint32_t n, int after_reset,
                                         cudaStream_t stream);
 
@@ -85,6 +88,10 @@ struct same_engine {
   uint32_t* d_state = nullptr;
   StreamBlob* d_blobs = nullptr;
   same_event* d_events = nullptr;
+  same_event* d_sorted = nullptr;        // arena events counting-sorted by (stream, seq) before read-back
+  uint32_t* d_sort_ws = nullptr;         // cnt[n+1] | start[n+1] | minseq[n] | bad[1]
+  bool pend_sorted = false;              // pend_events is one device-sorted batch: drain copies it as it is
+  int device_sort = 1;                   // option "device_sort": 0 = always sort on the host (diagnostic)
   uint8_t* d_payload = nullptr;
   unsigned int* d_counters = nullptr;
   unsigned int* h_counters = nullptr;   // pinned
@@ -121,9 +128,12 @@ int fail(same_engine* e, int code, const std::string& msg) {
 
 int alloc_arenas(same_engine* e, size_t max_events, size_t max_payload) {
   if (e->d_events) cudaFree(e->d_events);
+  if (e->d_sorted) cudaFree(e->d_sorted);
   if (e->d_payload) cudaFree(e->d_payload);
-  e->d_events = nullptr; e->d_payload = nullptr;
+  e->d_events = nullptr; e->d_sorted = nullptr; e->d_payload = nullptr;
   CK(e, cudaMalloc(&e->d_events, max_events * sizeof(same_event)));
+  CK(e, cudaMalloc(&e->d_sorted, max_events * sizeof(same_event)));
+  if (!e->d_sort_ws) CK(e, cudaMalloc(&e->d_sort_ws, (3 * (size_t)e->n_streams + 3) * sizeof(uint32_t)));
   CK(e, cudaMalloc(&e->d_payload, max_payload));
   e->events_cap = max_events; e->payload_cap = max_payload;
   e->p.events = e->d_events; e->p.payload = e->d_payload;
@@ -152,13 +162,28 @@ int collect(same_engine* e) {
     rc = fail(e, SAME_ERR_EVENT_OVERFLOW, buf);
   }
   const size_t cev = std::min(nev, e->events_cap), cpay = std::min(npay, e->payload_cap);
+  // big single batches are put into (stream, occurrence) order on the device; the host sort in drain is the fallback
+  const same_event* ev_src = e->d_events;
+  bool dev_sorted = false;
+  if (rc == SAME_OK && e->device_sort && cev >= 4096 && e->pend_events.empty() && cev <= 0xffffffffu) {
+    uint32_t* cnt = e->d_sort_ws;
+    uint32_t* start = cnt + e->n_streams + 1;
+    uint32_t* minseq = start + e->n_streams + 1;
+    uint32_t* bad = minseq + e->n_streams;
+    CK(e, same_launch_evsort(e->d_events, (uint32_t)cev, e->n_streams, cnt, minseq, start, e->d_sorted, bad, e->compute));
+    e->launches += 3;   // histogram, scan, scatter
+    CK(e, cudaMemcpyAsync(e->h_counters, bad, sizeof(unsigned int), cudaMemcpyDeviceToHost, e->compute));
+    CK(e, cudaStreamSynchronize(e->compute));
+    if (e->h_counters[0] == 0) { ev_src = e->d_sorted; dev_sorted = true; }
+  }
+  e->pend_sorted = dev_sorted || (cev == 0 && e->pend_sorted);
   if (cev) {
     // device -> pinned staging (two halves, so the copy of one slice overlaps the append of the other) -> pending lists
     const size_t base_ev = e->pend_events.size(), base_pay = e->pend_payload.size();
     e->pend_events.reserve(base_ev + cev);
     e->pend_payload.reserve(base_pay + cpay);
     const size_t half = STAGE_BYTES / 2;
-    const uint8_t* src[2] = {reinterpret_cast<const uint8_t*>(e->d_events), e->d_payload};
+    const uint8_t* src[2] = {reinterpret_cast<const uint8_t*>(ev_src), e->d_payload};
     const size_t bytes[2] = {cev * sizeof(same_event), cpay};
     for (int part = 0; part < 2; ++part) {
       size_t done = 0, queued = 0, qn[2] = {0, 0};
@@ -486,6 +511,8 @@ void same_engine_destroy(same_engine* e) {
   if (e->d_state) cudaFree(e->d_state);
   if (e->d_blobs) cudaFree(e->d_blobs);
   if (e->d_events) cudaFree(e->d_events);
+  if (e->d_sorted) cudaFree(e->d_sorted);
+  if (e->d_sort_ws) cudaFree(e->d_sort_ws);
   if (e->d_payload) cudaFree(e->d_payload);
   if (e->d_counters) cudaFree(e->d_counters);
   if (e->h_counters) cudaFreeHost(e->h_counters);
@@ -656,7 +683,9 @@ int same_engine_drain_events(same_engine* e, same_event* events, size_t events_c
     return fail(e, SAME_ERR_INVALID_ARG, "drain buffers too small");
   // per-stream order of occurrence, as iter_events yields them (receiver.rs:238-240, 267-269): counting sort by
   // stream straight into the caller's buffer, then order each stream's few events by sequence number
-  if (nev) {
+  if (nev && e->pend_sorted) {
+    memcpy(events, e->pend_events.data(), nev * sizeof(same_event));   // already in (stream, occurrence) order
+  } else if (nev) {
     std::vector<uint32_t> start(e->n_streams + 1, 0);
     for (const same_event& ev : e->pend_events) start[std::min(ev.stream, e->n_streams - 1) + 1] += 1;
     for (uint32_t i = 0; i < e->n_streams; ++i) start[i + 1] += start[i];
@@ -675,6 +704,7 @@ int same_engine_drain_events(same_engine* e, same_event* events, size_t events_c
   }
   if (npay) memcpy(payload, e->pend_payload.data(), npay);
   e->pend_events.clear(); e->pend_payload.clear();
+  e->pend_sorted = false;
   return SAME_OK;
 }
 
@@ -718,6 +748,7 @@ int same_engine_set_option(same_engine* e, const char* key, int value) {
   int rc = same_engine_sync(e);
   if (rc) return rc;
   if (strcmp(key, "force_generic") == 0) { e->force_generic = value; return SAME_OK; }
+  if (strcmp(key, "device_sort") == 0) { e->device_sort = value != 0; return SAME_OK; }
   if (strcmp(key, "lanes_per_warp") == 0) {
     if (!(value == 1 || value == 2 || value == 4 || value == 8 || value == 16 || value == 32))
       return fail(e, SAME_ERR_INVALID_ARG, "lanes_per_warp must be a power of two in 1..32");

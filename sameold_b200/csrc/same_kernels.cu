@@ -1136,6 +1136,53 @@ __global__ void same_init_kernel(const __grid_constant__ SameParams p, const uin
   st[(size_t)L.eq_fbc * L.n_pad] = __float_as_uint(1.0f);
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// Event read-back order: the host API hands events out per stream in order of occurrence (receiver.rs:238-240).  The
+// arena holds them in atomicAdd order, so they are counting-sorted by stream here before the device->host copy; within
+// a stream the position is seq - (first seq of this batch), sequence numbers being consecutive.
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void same_evsort_hist(const same_event* __restrict__ ev, uint32_t n, uint32_t n_streams,
+                                 uint32_t* __restrict__ cnt, uint32_t* __restrict__ minseq, uint32_t* __restrict__ bad) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t s = ev[i].stream;
+  if (s >= n_streams) { *bad = 1u; return; }
+  atomicAdd(&cnt[s], 1u);
+  atomicMin(&minseq[s], ev[i].seq);
+}
+// exclusive scan of cnt[0..n) into start[0..n], one block
+__global__ void __launch_bounds__(1024) same_evsort_scan(const uint32_t* __restrict__ cnt, uint32_t* __restrict__ start,
+                                                         uint32_t n) {
+  __shared__ uint32_t part[1024];
+  const uint32_t t = threadIdx.x, per = (n + 1023u) / 1024u;
+  const uint32_t lo = min(t * per, n), hi = min(lo + per, n);
+  uint32_t sum = 0;
+  for (uint32_t i = lo; i < hi; ++i) sum += cnt[i];
+  part[t] = sum;
+  __syncthreads();
+  for (uint32_t d = 1; d < 1024u; d <<= 1) {
+    const uint32_t v = t >= d ? part[t - d] : 0u;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  uint32_t run = part[t] - sum;   // exclusive prefix of this thread's range
+  for (uint32_t i = lo; i < hi; ++i) { start[i] = run; run += cnt[i]; }
+  if (t == 1023u) start[n] = part[1023];
+}
+__global__ void same_evsort_scatter(const same_event* __restrict__ ev, uint32_t n, uint32_t n_streams,
+                                    const uint32_t* __restrict__ start, const uint32_t* __restrict__ minseq,
+                                    same_event* __restrict__ out, uint32_t* __restrict__ bad) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const same_event e = ev[i];
+  if (e.stream >= n_streams) return;
+  const uint32_t k = e.seq - minseq[e.stream];
+  const uint32_t dst = start[e.stream] + k;
+  if (k >= start[e.stream + 1] - start[e.stream]) { *bad = 1u; return; }   // gap in the sequence numbers: host sorts
+  out[dst] = e;
+}
+
 }  // namespace same_dev
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -1171,6 +1218,22 @@ extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps,
     const size_t smem = (size_t)(128 + 2 * 64) * 32 * sizeof(float);
     same_dev::same_rx_generic_kernel<128, 64><<<blocks, 32, smem, stream>>>(*p, *taps, d_samples, d_offsets, d_lengths);
   }
+  return cudaGetLastError();
+}
+
+// Counting sort of `n` arena events by (stream, seq) into `d_sorted`; *d_bad != 0 afterwards means "not sorted, use
+// the arena order and sort on the host".  d_cnt / d_start: n_streams + 1 words, d_minseq: n_streams words.
+extern "C" cudaError_t same_launch_evsort(const same_event* d_events, uint32_t n, uint32_t n_streams, uint32_t* d_cnt,
+                                          uint32_t* d_minseq, uint32_t* d_start, same_event* d_sorted, uint32_t* d_bad,
+                                          cudaStream_t stream) {
+  cudaError_t err;
+  if ((err = cudaMemsetAsync(d_cnt, 0, ((size_t)n_streams + 1) * 4, stream)) != cudaSuccess) return err;
+  if ((err = cudaMemsetAsync(d_minseq, 0xff, (size_t)n_streams * 4, stream)) != cudaSuccess) return err;
+  if ((err = cudaMemsetAsync(d_bad, 0, 4, stream)) != cudaSuccess) return err;
+  const uint32_t blocks = (n + 255u) / 256u;
+  same_dev::same_evsort_hist<<<blocks, 256, 0, stream>>>(d_events, n, n_streams, d_cnt, d_minseq, d_bad);
+  same_dev::same_evsort_scan<<<1, 1024, 0, stream>>>(d_cnt, d_start, n_streams);
+  same_dev::same_evsort_scatter<<<blocks, 256, 0, stream>>>(d_events, n, n_streams, d_start, d_minseq, d_sorted, d_bad);
   return cudaGetLastError();
 }
 

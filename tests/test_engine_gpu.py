@@ -359,6 +359,37 @@ def test_config3_full_size_kernels_agree_and_are_deterministic():
         assert msgs and bytes(msgs[0].data).decode("ascii") == plans[s_].header, f"stream {s_}"
 
 
+def test_device_and_host_event_sort_agree():
+    """Events come back per stream in order of occurrence; big batches are ordered on the device, small or accumulated
+    ones on the host.  Both must give the same array, element for element, also across two submits before a drain."""
+    _torch()
+    ns = 3000
+    buf, plans, n, stride = _device_corpus(ns, 24.0, first=9000)
+    offsets = np.arange(ns, dtype=np.uint64) * np.uint64(stride)
+    lengths = np.full(ns, n, np.uint32)
+    half = np.full(ns, n // 2, np.uint32)
+    b = sb.SameReceiverBuilder.samedec(22050)
+    out = []
+    for device_sort, split in ((1, False), (0, False), (1, True)):
+        rx = b.build_batch(ns)
+        rx.set_option("device_sort", device_sort)
+        if split:   # two collects before the drain: the second batch is merged on the host
+            rx.submit_device(buf.data_ptr(), ns * stride, offsets, half)
+            rx.sync()
+            rx.submit_device(buf.data_ptr(), ns * stride, offsets + np.uint64(n // 2), lengths - half)
+            rx.sync()
+        else:
+            rx.submit_device(buf.data_ptr(), ns * stride, offsets, lengths)
+            rx.sync()
+        evs, pay = rx.drain_raw()
+        assert evs.size > 4096
+        key = evs["stream"].astype(np.uint64) << np.uint64(32) | evs["seq"].astype(np.uint64)
+        assert np.all(np.diff(key.astype(np.int64)) > 0), "sorted by (stream, occurrence), no duplicates"
+        out.append(_canonical_raw(evs, pay))
+    for other in out[1:]:
+        assert np.array_equal(out[0][0], other[0]) and np.array_equal(out[0][1], other[1])
+
+
 def test_long_single_stream_in_time_chunks():
     """Config 5 shape (one continuous stream, sparse bursts), shortened to 16 minutes: clusters of SAME bursts separated
     by minutes of noise, fed in 60 s chunks to a one-stream engine; events and messages must equal the oracle's."""
