@@ -470,20 +470,24 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// Warp-specialised fast kernel: the same algorithm as same_rx_fast_kernel, split over two warps per 32 streams.
+// Three-warp kernel: the same algorithm as same_rx_fast_kernel, split over three warps per 32 streams.
 //
-//   warp 1 (producer)  raw s16 -> exact DC-blocked f32 into the d ring (A0, A1): vector loads with one chunk of
-//                      prefetch, integer recursion in registers.  Runs ahead of the consumer by up to the ring size.
-//   warp 0 (consumer)  AGC, matched filters, timing loop, squelch, byte path, events (A2-A9).
+//   warp 1 (producer)    raw s16 -> exact DC-blocked f32 into the d ring (A0, A1): vector loads with one chunk of
+//                        prefetch, integer recursion in registers.  Runs ahead of the consumer by up to the ring size.
+//   warp 2 (look-ahead)  while the consumer is busy with round r, the AGC recurrence of the next WS_SPEC samples
+//                        (the segment of round r+1) into the y ring, the gain after every sample into a gain ring
+//                        (A2, A3).  Exact speculation: see the comment at its loop.
+//   warp 0 (consumer)    picks up the look-ahead (or runs the recurrence itself when it does not apply), matched
+//                        filters, timing loop, squelch, byte path, events (A4-A9).
 //
-// The two warps sit on different schedulers of the SM, so the refill (global-load latency + ~11 instructions per
-// sample) leaves the consumer's critical path, and each warp needs about half the registers of the fused kernel, which
-// doubles the number of streams resident per SM.  Hand-off: per-lane counters in shared memory (producer publishes
-// `rp`, consumer publishes `pos`) and two named barriers used in strict alternation — no polling, no sleeping:
-//     consumer round:  bar.sync B_DATA  -> segment (reads d) -> publish pos -> bar.arrive B_POS -> filters/TED/symbol
-//     producer round:  bar.sync B_POS   -> refill lanes that have room      -> publish rp  -> bar.arrive B_DATA
-// so the refill for round r+1 overlaps the matched-filter half of round r, and after every refill each lane holds at
-// least one full segment (>= 32 samples) of data.
+// The warps sit on different schedulers of the SM, so the refill (global-load latency + ~11 instructions per sample)
+// and the AGC chain leave the consumer's critical path.  Hand-off: per-lane counters in shared memory and three named
+// barriers used in strict alternation — no polling, no sleeping:
+//     consumer:    bar.sync B_DATA, B_LA -> segment -> publish pos, gain, flag -> bar.arrive B_POS -> filters/TED/symbol
+//     producer:    bar.sync B_POS -> refill lanes that have room -> publish rp -> bar.arrive B_DATA
+//     look-ahead:  bar.sync B_POS -> recurrence over WS_SPEC samples              -> bar.arrive B_LA
+// so the refill and the look-ahead for round r+1 overlap the matched-filter half of round r, and after every refill
+// each lane holds at least one full segment (>= 32 samples) of data.
 // ----------------------------------------------------------------------------------------------------------------
 #define WS_DRING 128       // d ring slots of the warp-specialised kernel
 #define WS_SPEC 22         // look-ahead samples: 42 taps + 22 new samples just fit the 64-slot y ring; covers most whole segments
