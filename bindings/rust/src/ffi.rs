@@ -57,6 +57,39 @@ pub struct same_engine {
     _private: [u8; 0],
 }
 
+/// Opaque copy of the resident state of all streams (`SameReceiver: Clone`, receiver.rs:70).
+#[repr(C)]
+pub struct same_snapshot {
+    _private: [u8; 0],
+}
+
+/// One demodulated symbol (SymbolEstimate.data, symsync.rs:52-59): diagnostic tap.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct same_soft_symbol {
+    pub input_sample_counter: u64,
+    pub zero: f32,
+    pub sym: f32,
+}
+
+/// Constants the engine derived from the configuration (for parity checks against the CPU receiver).
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct same_derived {
+    pub sps: f32,
+    pub agc_bw: f32,
+    pub agc_gain0: f32,
+    pub samples_per_ted: f32,
+    pub period_min: f32,
+    pub period_max: f32,
+    pub alpha_unlocked: f32,
+    pub beta_unlocked: f32,
+    pub alpha_locked: f32,
+    pub beta_locked: f32,
+    pub dc_len: u32,
+    pub ntaps: u32,
+}
+
 extern "C" {
     pub fn same_abi_version() -> u32;
     pub fn same_config_default(cfg: *mut same_config, input_rate: u32);
@@ -79,4 +112,23 @@ extern "C" {
                                     payload: *mut u8, payload_cap: usize, n_payload: *mut usize) -> c_int;
     pub fn same_host_alloc(bytes: usize) -> *mut c_void;
     pub fn same_host_free(p: *mut c_void);
+    // samples already on the device (the engine's own corpus generator, or another CUDA producer)
+    pub fn same_engine_submit_s16_device(e: *mut same_engine, d_samples: *const i16, total_samples: u64, offsets: *const u64,
+                                         lengths: *const u32) -> c_int;
+    pub fn same_engine_cuda_stream(e: *mut same_engine) -> *mut c_void;
+    // SameReceiver: Clone  (used by flush() to stop at the sample of the first message)
+    pub fn same_engine_snapshot(e: *mut same_engine, out: *mut *mut same_snapshot) -> c_int;
+    pub fn same_engine_restore(e: *mut same_engine, snap: *const same_snapshot) -> c_int;
+    pub fn same_snapshot_free(snap: *mut same_snapshot);
+    pub fn same_engine_set_event_capacity(e: *mut same_engine, max_events: usize, max_payload_bytes: usize) -> c_int;
+    // diagnostics
+    pub fn same_engine_enable_soft_trace(e: *mut same_engine, cap_per_stream: u32) -> c_int;
+    pub fn same_engine_read_soft_trace(e: *mut same_engine, stream: u32, out: *mut same_soft_symbol, cap: usize, n: *mut usize) -> c_int;
+    pub fn same_engine_set_option(e: *mut same_engine, key: *const c_char, value: c_int) -> c_int;
+    pub fn same_engine_last_timing(e: *mut same_engine, h2d_ms: *mut f32, kernel_ms: *mut f32) -> c_int;
+    pub fn same_engine_launch_count(e: *const same_engine) -> u64;
+    pub fn same_engine_timer_start(e: *mut same_engine) -> c_int;
+    pub fn same_engine_timer_stop(e: *mut same_engine, elapsed_ms: *mut f32) -> c_int;
+    pub fn same_engine_get_derived(e: *const same_engine, d: *mut same_derived, mark_re_im: *mut f32, space_re_im: *mut f32,
+                                   cap_taps: usize) -> c_int;
 }

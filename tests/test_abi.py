@@ -110,3 +110,31 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "same_oracle" not in txt and "liboracle" not in txt and "from oracle" not in txt \
                     and "import oracle" not in txt, f"{f} references the oracle"
+
+
+def test_rust_ffi_declares_the_whole_header():
+    """bindings/rust/src/ffi.rs (source only: no Rust toolchain here) must declare every function of the C header,
+    and its #[repr(C)] structs must list the header's fields in the same order."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "same_engine.h")).read()
+    ffi = open(os.path.join(ROOT, "bindings", "rust", "src", "ffi.rs")).read()
+    c_fns = set(re.findall(r"^[A-Za-z_][A-Za-z0-9_ \*]*?\b(same_[a-z0-9_]+)\s*\(", hdr, flags=re.M))
+    rust_fns = set(re.findall(r"pub fn (same_[a-z0-9_]+)", ffi))
+    assert c_fns and c_fns == rust_fns, (sorted(c_fns - rust_fns), sorted(rust_fns - c_fns))
+
+    def c_fields(name):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, flags=re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                out += [f.strip() for f in decl.split(None, 1)[1].split(",")]
+        return out
+
+    def rust_fields(name):
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % name, ffi, flags=re.S).group(1)
+        return re.findall(r"pub ([a-z0-9_]+):", body)
+
+    for name in ("same_config", "same_event", "same_soft_symbol", "same_derived"):
+        assert c_fields(name) == rust_fields(name), name
