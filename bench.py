@@ -14,7 +14,13 @@ only for the barrier and the max-over-ranks of the measured time.
   cpu_baseline  the CPU oracle (C++ restatement of sameold 0.6.0, one stream per host thread) on a bounded sample of the
             same corpus — `kind: "port"` (the Rust reference cannot be built here)
 
+  config4   (extra key of the same line) BASELINE config 4: 65 536 streams x 60 s in TOTAL (173 GB), contiguous shards
+            of 65 536/N streams per rank, streamed through in 5 s time-chunks with the receiver state resident
+            (strong scaling); device-resident and host-buffer numbers like `value` / `e2e`
+  e2e.h2d_ceiling_gbs  bare pinned host->device copy rate of all ranks at once (no kernel): what `e2e` is bounded by
+
 `--impl reference` times that CPU implementation alone (rank 0 only), same metric/config.
+`--config 5` runs BASELINE config 5 (one 24 h stream) on one GPU and prints its own line.
 """
 import argparse
 import json
@@ -49,6 +55,13 @@ def parse_args():
     ap.add_argument("--no-bursts", action="store_true", help="diagnostic: noise-only corpus (not a valid bench line)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="skip the config-4 leg (65536 streams, time-chunked, sharded)")
+    ap.add_argument("--config", type=int, default=3, choices=[3, 5], help="5: the single 24 h stream (own JSON line)")
+    ap.add_argument("--hours", type=float, default=24.0, help="--config 5 stream length")
+    ap.add_argument("--config4-streams", type=int, default=65536)
+    ap.add_argument("--config4-chunk-seconds", type=float, default=5.0)
+    ap.add_argument("--kernel", type=int, default=0, help="diagnostic: engine option 'kernel' (0 = measured policy)")
+    ap.add_argument("--lanes-per-warp", type=int, default=0, help="diagnostic: engine option 'lanes_per_warp'")
     return ap.parse_args()
 
 
@@ -151,28 +164,80 @@ def cpu_baseline(host_samples, cfg, cores):
     return audio / best, best, int(nb.sum()), int(nm.sum())
 
 
-def bind_to_gpu_numa_node(device):
-    """Pin this process (and therefore its first-touch host allocations, the pinned sample buffer above all) to the CPU
-    cores of the NUMA node the GPU hangs off, so that with one rank per GPU the host->device copies of different
-    ranks do not cross the socket interconnect.  Best effort; returns the node or None."""
+def _cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if part:
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_cpus(device, local_rank, local_world):
+    """Pin this process — and with it the first-touch placement of its pinned sample pool, allocated afterwards — to
+    host cores next to its GPU, so that with one rank per GPU the host->device copies of different ranks do not cross
+    the socket interconnect and the ranks' host threads do not migrate onto each other.  In order: the NUMA node sysfs
+    reports for the GPU; the CPU affinity NVML reports for it (what `nvidia-smi topo -m` prints); an even split of
+    the allowed cores per local rank (single-node VMs report neither).  Returns a description for the bench line."""
+    allowed = os.sched_getaffinity(0)
     try:
         import torch
         props = torch.cuda.get_device_properties(device)
         bus = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
         node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
-        if node < 0:
-            return None
-        cpus = set()
-        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if not cpus:
-            return None
-        os.sched_setaffinity(0, cpus)
-        return node
+        if node >= 0:
+            cpus = _cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read()) & allowed
+            if cpus and len(cpus) < len(allowed):
+                os.sched_setaffinity(0, cpus)
+                return {"how": "sysfs numa_node", "node": node, "cpus": len(cpus)}
     except Exception:
-        return None
+        pass
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(device)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(("%08X:%02X:%02X.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)).encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1} & allowed
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return {"how": "nvml cpu affinity", "node": None, "cpus": len(cpus)}
+    except Exception:
+        pass
+    try:
+        cores = sorted(allowed)
+        per = max(1, len(cores) // max(1, local_world))
+        mine = set(cores[local_rank * per:(local_rank + 1) * per]) or set(cores)
+        os.sched_setaffinity(0, mine)
+        return {"how": "even split of allowed cores (no NUMA information on this box)", "node": None, "cpus": len(mine)}
+    except Exception:
+        return {"how": "unbound", "node": None, "cpus": len(allowed)}
+
+
+def kernel_source_sha16():
+    """Hash of the receiver-kernel sources: ties profiles/rx_kernel_traffic.json (an ncu capture) to the code it was
+    taken from, so a stale capture is dropped instead of silently reported."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("same_kernels.cu", "same_lane.cuh", "same_transport.cuh", "same_params.h"):
+        with open(os.path.join(ROOT, "sameold_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def profiled_traffic(ns, seconds):
+    """(dram bytes per launch from the committed ncu capture or None, note)."""
+    tpath = os.path.join(ROOT, "profiles", "rx_kernel_traffic.json")
+    try:
+        tj = json.load(open(tpath))
+    except Exception:
+        return None, "no ncu capture committed"
+    if tj.get("streams") != ns or abs(tj.get("seconds", 0) - seconds) > 1e-9:
+        return None, "ncu capture is for another workload"
+    if tj.get("kernel_src_sha16") != kernel_source_sha16():
+        return None, f"ncu capture of {tj.get('captured', '?')} predates the current kernel sources (stale): dropped"
+    return tj.get("dram_bytes_per_launch"), f"ncu --set full capture of {tj.get('captured', '?')} ({tj.get('report', '')})"
 
 
 def main():
@@ -180,6 +245,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     n_samples = int(args.seconds * RATE)
     cfgname = {"workload": workload_name(args.streams, args.seconds), "streams_per_gpu": args.streams,
                "seconds": args.seconds, "rate_hz": RATE, "receiver_config": "samedec (main.rs:29-37)",
@@ -196,7 +262,8 @@ def main():
     from sameold_b200 import synth, _lib
 
     torch.cuda.set_device(local_rank)
-    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    binding = bind_host_cpus(local_rank, local_rank, local_world) if world > 1 else {"how": "single rank: unbound", "node": None,
+                                                                                      "cpus": len(os.sched_getaffinity(0))}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -219,6 +286,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    comm = {"world": world, "rank": rank, "local_rank": local_rank, "barrier": barrier, "max": max_over_ranks,
+            "sum": sum_over_ranks}
+    if args.config == 5:
+        return run_config5(args, comm)
+
     # ---- synthetic corpus, resident in HBM ----
     ns = args.streams
     stride = (n_samples + 7) // 8 * 8
@@ -233,6 +305,12 @@ def main():
 
     builder = sb.SameReceiverBuilder.samedec(RATE)
     rx = builder.build_batch(ns, device=local_rank)
+    if args.kernel:
+        rx.set_option("kernel", args.kernel)
+    if args.lanes_per_warp:
+        rx.set_option("lanes_per_warp", args.lanes_per_warp)
+    kernel_names = {1: "same_rx_generic_kernel", 2: "same_rx_fast_kernel", 3: "same_rx_pipe_kernel", 4: "same_rx_ws_kernel"}
+    kernel_name = kernel_names.get(rx.get_option("kernel_selected"), "same_rx_kernel")
     audio_per_step = ns * n_samples / RATE
 
     def step_device():
@@ -276,30 +354,24 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     k_ms = statistics.mean(kernel_ms)
     achieved = (2.0 * ns * n_samples) / (k_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "rx_kernel_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            tj = json.load(open(tpath))
-            if tj.get("streams") == ns and abs(tj.get("seconds", 0) - args.seconds) < 1e-9:
-                traffic = tj.get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": "same_rx_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
-                "kernel_ms_per_launch": round(k_ms, 3), "algorithmic_bytes_per_launch": 2 * ns * n_samples,
-                "note": "fused per-lane receiver loop is issue/latency-bound, not HBM-bound (DESIGN.md §5)"}
+    traffic, traffic_note = profiled_traffic(ns, args.seconds)
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 5), "traffic": traffic, "traffic_source": traffic_note,
+                "peak_source": peak_src, "kernel_ms_per_launch": round(k_ms, 3),
+                "algorithmic_bytes_per_launch": 2 * ns * n_samples,
+                "note": "fused per-lane receiver loop is issue/latency-bound, not HBM-bound (DESIGN.md §5); the HBM-bound "
+                        "feed-forward kernel (same_frontend_kernel) is measured in profiles/"}
 
     # ---- e2e: host buffers through the C ABI, H2D + event D2H inside the timed region ----
     e2e = None
     host_np = None
+    lib = _lib.load()
+    import ctypes as C
     if not args.no_e2e:
-        lib = _lib.load()
         nbytes = ns * stride * 2
         hptr = lib.same_host_alloc(nbytes)
         if not hptr:
             raise RuntimeError("pinned host allocation failed")
-        import ctypes as C
         host_np = np.ctypeslib.as_array(C.cast(hptr, C.POINTER(C.c_int16)), shape=(ns, stride))
         # same corpus, now in pinned host memory (copied out once, untimed)
         host_t = torch.from_numpy(host_np)
@@ -327,22 +399,52 @@ def main():
         e2e_ms = rx.timer_stop()
         barrier()
         e2e_ms = max_over_ranks(e2e_ms)
+        # the ceiling: the same bytes in the same strided chunks, every rank at once, no kernel
+        ms = C.c_float()
+        barrier()
+        width = (bounds[1] - bounds[0]) * 2
+        rc = lib.same_h2d_probe(local_rank, C.c_void_p(hptr), stride * 2, width, ns, nchunk, C.byref(ms))
+        barrier()
+        probe_ms = max_over_ranks(ms.value if rc == 0 else float("nan"))
+        ceiling_gbs = world * ns * width * nchunk / (probe_ms * 1e-3) / 1e9
+        e2e_gbs = world * ns * n_samples * 2 * args.steps / (e2e_ms * 1e-3) / 1e9
         e2e = {"value": round(audio_per_step * args.steps * world / (e2e_ms * 1e-3), 1), "unit": UNIT,
                "h2d_bytes_per_step": int(ns * n_samples * 2 + nchunk * ns * 12) * world,
                "d2h_bytes_per_step": int(sum_over_ranks(statistics.mean(d2h_bytes))), "ms_per_step": round(e2e_ms / args.steps, 3),
                "chunks_per_step": nchunk, "api": "same_engine_submit_s16_2d + sync + drain_events (pinned host buffer)",
-               "rank0_numa_node": numa_node}
+               "h2d_gbs": round(e2e_gbs, 2), "h2d_ceiling_gbs": round(ceiling_gbs, 2),
+               "frac_of_h2d_ceiling": round(e2e_gbs / ceiling_gbs, 4),
+               "h2d_ceiling_how": f"same_h2d_probe: {nchunk} strided copies of {ns} rows x {width} B per rank from the same pinned "
+                                  f"buffer, all {world} ranks at once, no kernel, max over ranks",
+               "host_binding": binding}
 
-    # ---- CPU baseline on rank 0 at N=1 ----
+    # ---- CPU baseline (rank 0's host cores; the other ranks wait) ----
     cpu = None
-    if not args.no_cpu and world == 1 and rank == 0:
-        k = min(args.cpu_sample_streams, ns)
-        sample = buf[:k, :n_samples].cpu().numpy()
-        cores = os.cpu_count() or 1
-        v, secs, nb, nm = cpu_baseline(sample, builder.config(), cores)
-        cpu = {"value": round(v, 1), "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"first {k} streams x {args.seconds:g} s of this workload, one receiver per stream, {cores} threads, best of 2 ({secs:.2f} s)",
-               "what": "oracle/ C++ restatement of sameold 0.6.0 (link + transport layers), g++ -O2 -ffp-contract=off; the Rust crate cannot be built here"}
+    if not args.no_cpu:
+        if rank == 0:
+            k = min(args.cpu_sample_streams, ns)
+            sample = buf[:k, :n_samples].cpu().numpy()
+            cores = len(os.sched_getaffinity(0)) if world > 1 else (os.cpu_count() or 1)
+            v, secs, nb, nm = cpu_baseline(sample, builder.config(), cores)
+            cpu = {"value": round(v, 1), "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"first {k} streams x {args.seconds:g} s of this workload, one receiver per stream, {cores} threads, best of 2 ({secs:.2f} s)",
+                   "what": "oracle/ C++ restatement of sameold 0.6.0 (link + transport layers), g++ -O2 -ffp-contract=off; the Rust crate cannot be built here"}
+            del sample
+        barrier()
+
+    # ---- config 4: 65 536 streams in total, sharded over the ranks, time-chunked ----
+    del buf
+    if host_np is not None:
+        del host_np, host_t
+        lib.same_host_free(hptr)
+    del rx
+    torch.cuda.empty_cache()
+    config4 = None
+    if not args.no_config4 and not args.no_bursts:
+        try:
+            config4 = run_config4(args, comm, peak)
+        except Exception as e:  # the main line must survive a failure of the extra leg
+            config4 = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         line = {
@@ -352,53 +454,201 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "wall_ms_per_step": round(wall_ms / args.steps, 3), "events_per_step": n_events,
             "headers_decoded_per_step": n_headers, "realtime_factor_per_gpu": round(value / world, 1),
+            "config4": config4,
         }
         print(json.dumps(line))
-    if host_np is not None:
-        del host_np
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
-def run_reference(args, cfgname, n_samples):
-    """The reference's CPU implementation of the path (oracle port) on all host threads; each step = a bounded sample
-    (cpu_sample_streams streams) of the same workload."""
-    from oracle import Oracle
-    from sameold_b200 import synth, _lib
+def run_config4(args, comm, peak):
+    """BASELINE config 4: `config4_streams` (65 536) synthetic 60 s streams in TOTAL; rank r owns the contiguous shard
+    [r*S/N, (r+1)*S/N) (one engine, one CUDA stream pair); the 173 GB of samples do not fit one GPU, so every rank
+    streams its shard through in `chunk_seconds` time-chunks with the receiver state resident (chunked == whole,
+    receiver.rs:233-274).  STRONG scaling: the total is fixed.  Two timings, both summed over the chunks and taken as
+    the max over ranks:
+      value  each chunk generated on the device (untimed), then submit + sync + drain timed with CUDA events
+      e2e    each chunk staged in pinned host memory (untimed), then submit_s16_2d in 4 column slices (copy of slice
+             k+1 overlaps the kernel of slice k) + sync + drain, timed with CUDA events"""
     import ctypes as C
+    import torch
+    import sameold_b200 as sb
+    from sameold_b200 import synth, _lib
+    world, rank, local_rank = comm["world"], comm["rank"], comm["local_rank"]
+    total = args.config4_streams
+    first, last = total * rank // world, total * (rank + 1) // world
+    ns = last - first
+    secs = 60.0
+    cn = int(args.config4_chunk_seconds * RATE) // 8 * 8
+    n = int(secs * RATE)
+    nchunks = (n + cn - 1) // cn
+    plans = synth.plan_corpus(ns, RATE, secs, first_stream=first)
+    corpus = synth.DeviceCorpus(plans, RATE, device=local_rank)
+    buf = torch.empty((ns, cn), dtype=torch.int16, device="cuda")
+    rx = sb.SameReceiverBuilder.samedec(RATE).build_batch(ns, device=local_rank)
+    kernel = rx.get_option("kernel_selected")
+    offsets = np.arange(ns, dtype=np.uint64) * np.uint64(cn)
+    lib = _lib.load()
+
+    def pass_device():
+        rx.reset()
+        ms_sum, k_sum, headers = 0.0, 0.0, 0
+        for c in range(nchunks):
+            w = min(cn, n - c * cn)
+            corpus.generate(buf.data_ptr(), cn, w, first_sample=c * cn)
+            lengths = np.full(ns, w, np.uint32)
+            rx.timer_start()
+            rx.submit_device(buf.data_ptr(), ns * cn, offsets, lengths)
+            rx.sync()
+            ev, _ = rx.drain_raw(reuse=True)
+            ms_sum += rx.timer_stop()
+            k_sum += rx.last_timing()[1]
+            headers += int((ev["kind"] == 18).sum())
+        return ms_sum, k_sum, headers
+
+    pass_device()                                  # warm-up pass (also warms the generator)
+    comm["barrier"]()
+    launches0 = rx.launch_count()
+    dev_ms, k_ms, headers = pass_device()
+    launches = rx.launch_count() - launches0
+    comm["barrier"]()
+    dev_ms_max = comm["max"](dev_ms)
+    k_ms_max = comm["max"](k_ms)
+    headers_all = int(comm["sum"](headers))
+    assert headers_all >= int(0.95 * total), f"config 4 corpus not decoded: {headers_all} headers of {total}"
+    audio = total * secs
+    out = {"workload": f"config4: {total} synthetic 60 s streams in total @22050 Hz s16le (173 GB), contiguous shards of "
+                       f"{total}//{world} streams per GPU, {nchunks} time-chunks of {cn / RATE:g} s, state resident; same "
+                       f"generator as config 3 (seed 0x5A3E0000+stream_id)",
+           "streams_total": total, "streams_per_gpu": ns, "chunk_seconds": cn / RATE, "chunks": nchunks,
+           "scaling": "strong", "value": round(audio / (dev_ms_max * 1e-3), 1), "unit": UNIT,
+           "ms_total": round(dev_ms_max, 2), "kernel_ms_total": round(k_ms_max, 2), "kernel": kernel,
+           "roofline_frac": round(2.0 * ns * n / (k_ms * 1e-3) / 1e9 / peak, 5),
+           "headers_decoded": headers_all, "gpu_launches": int(launches)}
+    if not args.no_e2e:
+        hptr = lib.same_host_alloc(ns * cn * 2)
+        if not hptr:
+            raise RuntimeError("pinned host allocation failed")
+        try:
+            host_t = torch.from_numpy(np.ctypeslib.as_array(C.cast(hptr, C.POINTER(C.c_int16)), shape=(ns, cn)))
+            nsl = 4
+            rx.reset()
+            e2e_ms, headers, d2h = 0.0, 0, 0
+            for c in range(nchunks):
+                w = min(cn, n - c * cn)
+                corpus.generate(buf.data_ptr(), cn, w, first_sample=c * cn)
+                host_t.copy_(buf)
+                torch.cuda.synchronize()
+                cuts = [int(round(i * w / nsl)) for i in range(nsl + 1)]
+                rx.timer_start()
+                for i in range(nsl):
+                    rx.submit_2d(hptr, cn, cuts[i], cuts[i + 1] - cuts[i])
+                rx.sync()
+                ev, pay = rx.drain_raw(reuse=True)
+                e2e_ms += rx.timer_stop()
+                headers += int((ev["kind"] == 18).sum())
+                d2h += 48 * int(ev.size) + int(pay.size)
+            comm["barrier"]()
+            e2e_max = comm["max"](e2e_ms)
+            assert int(comm["sum"](headers)) == headers_all, "config 4 host path decodes differently"
+            out["e2e"] = {"value": round(audio / (e2e_max * 1e-3), 1), "unit": UNIT, "ms_total": round(e2e_max, 2),
+                          "h2d_bytes_per_step": int(total * n * 2), "d2h_bytes_per_step": int(comm["sum"](d2h)),
+                          "h2d_gbs": round(total * n * 2 / (e2e_max * 1e-3) / 1e9, 2),
+                          "api": f"same_engine_submit_s16_2d x {nsl} per chunk + sync + drain_events"}
+        finally:
+            del host_t
+            lib.same_host_free(hptr)
+    del rx, buf
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_config5(args, comm):
+    """BASELINE config 5: ONE continuous stream of `--hours` (24) hours, a SAME event every U(10,60) minutes, decoded by a
+    one-stream engine in 10-minute chunks from device memory.  A single stream is strictly sequential
+    (receiver.rs:243): one lane of one warp — the number is the single-stream realtime factor (replicas only)."""
+    import torch
+    import sameold_b200 as sb
+    from sameold_b200 import synth
+    if comm["rank"] != 0:
+        return 0
+    n = int(args.hours * 3600 * RATE)
+    plan = synth.plan_long_stream(args.hours, RATE)
+    buf = torch.empty(((n + 7) // 8 * 8,), dtype=torch.int16, device="cuda")
+    synth.DeviceCorpus([plan], RATE, device=comm["local_rank"]).generate(buf.data_ptr(), buf.numel(), n)
+    rx = sb.SameReceiverBuilder.samedec(RATE).build_batch(1, device=comm["local_rank"])
+    if args.kernel:
+        rx.set_option("kernel", args.kernel)
+    step = 600 * RATE
+    zero = np.zeros(1, np.uint64)
+    sampler = ClockSampler(comm["local_rank"])
+
+    def one_pass():
+        rx.reset()
+        msgs, k_ms = 0, 0.0
+        rx.timer_start()
+        for lo in range(0, n, step):
+            k = min(step, n - lo)
+            rx.submit_device(buf.data_ptr() + 2 * lo, k, zero, np.array([k], np.uint32))
+            rx.sync()
+            ev, _ = rx.drain_raw(reuse=True)
+            msgs += int(((ev["kind"] == 18) | (ev["kind"] == 19)).sum())
+            k_ms += rx.last_timing()[1]
+        return rx.timer_stop(), k_ms, msgs
+
+    sampler.start()
+    ms, k_ms, msgs = one_pass()
+    clocks = sampler.stop()
+    cpu = None
+    if not args.no_cpu:
+        from oracle import Oracle
+        sample = buf[: min(n, 3600 * RATE)].cpu().numpy()
+        o = Oracle(oracle_config_from(sb.SameReceiverBuilder.samedec(RATE).config()))
+        t0 = time.perf_counter()
+        o.process_s16(sample)
+        secs = time.perf_counter() - t0
+        cpu = {"value": round(sample.size / RATE / secs, 1), "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"first {sample.size / RATE / 3600:g} h of this stream on one host core ({secs:.2f} s)"}
+    line = {"metric": METRIC, "value": round(n / RATE / (ms * 1e-3), 1), "unit": UNIT, "n_gpus": 1, "steps": 1, "warmup": 0,
+            "ms_per_step": round(ms, 1), "higher_is_better": True, "scaling": "replicas only (a single stream does not shard)",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"config5: one continuous {args.hours:g} h stream @22050 Hz s16le ({n} samples), "
+                                   f"{len(plan.burst_starts)} bursts (a SAME event every U(10,60) min), AWGN 10 dB SNR; "
+                                   f"one-stream engine, 10-minute chunks from device memory", "hours": args.hours},
+            "kernel_ms_total": round(k_ms, 1), "messages_decoded": msgs, "events_planned": len(plan.burst_starts) // 6,
+            "realtime_factor_single_stream": round(n / RATE / (ms * 1e-3), 1), "cpu_baseline": cpu, "clocks": clocks,
+            "gpu_launches": int(rx.launch_count())}
+    print(json.dumps(line))
+    return 0
+
+
+def run_reference(args, cfgname, n_samples):
+    """The reference's CPU implementation of the path (oracle port) on all host threads, on the SAME config (`streams`
+    streams x `seconds`); the corpus comes from the CPU generator in oracle/ (same signal model as the device
+    generator), so this arm loads no GPU code at all.  The C++ restatement of sameold 0.6.0 stands in for the Rust
+    crate, which cannot be built here (no cargo/rustc, crates not vendored)."""
+    from oracle import decode_batch_events, synth_cpu
+    from oracle.pyoracle import default_config
+    from sameold_b200 import synth          # pure-Python stream plans only; the native library is not loaded
     cores = os.cpu_count() or 1
-    k = min(args.cpu_sample_streams, args.streams)
-    cfg = _lib.SameConfig()
-    _lib.load().same_config_samedec(C.byref(cfg), RATE)
+    k = args.streams
     plans = synth.plan_corpus(k, RATE, args.seconds, first_stream=0)
-    try:
-        import torch
-        have_gpu = torch.cuda.is_available()
-    except Exception:
-        have_gpu = False
-    if have_gpu:
-        import torch
-        stride = (n_samples + 7) // 8 * 8
-        buf = torch.empty((k, stride), dtype=torch.int16, device="cuda")
-        synth.generate_on_device(plans, buf.data_ptr(), stride, n_samples, RATE, device=0)
-        sample = buf[:, :n_samples].cpu().numpy()
-        del buf
-        how = "device generator"
-    else:
-        k = min(k, 16)
-        sample = np.stack([synth.render_numpy(p, n_samples, RATE) for p in plans[:k]])
-        how = "numpy generator (no GPU visible)"
-    ocfg = oracle_config_from(cfg)
-    audio = sample.shape[0] * n_samples / RATE
-    for _ in range(min(args.warmup, 1)):
-        Oracle.decode_batch(ocfg, sample, cores)
     t0 = time.perf_counter()
-    secs_total = 0.0
+    sample = synth_cpu(plans, n_samples, RATE, cores)
+    gen_s = time.perf_counter() - t0
+    ocfg = default_config(RATE, samedec=True)
+    audio = k * n_samples / RATE
+    for _ in range(args.warmup):
+        decode_batch_events(ocfg, sample, cores)
+    t0 = time.perf_counter()
+    secs_total, n_som = 0.0, 0
     for _ in range(args.steps):
-        secs, nb, nm = Oracle.decode_batch(ocfg, sample, cores)
+        ev, _pay, secs = decode_batch_events(ocfg, sample, cores)
         secs_total += secs
+        n_som = int((ev["kind"] == 18).sum())
     wall = time.perf_counter() - t0
+    assert args.seconds < 60.0 or n_som >= int(0.9 * k), "reference arm did not decode its corpus"
     value = audio * args.steps / secs_total
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus,
@@ -406,9 +656,12 @@ def run_reference(args, cfgname, n_samples):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": cfgname,
         "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample.shape[0]} streams x {args.seconds:g} s per step ({how}), one receiver per stream, {cores} threads"},
+                         "sample": f"all {k} streams x {args.seconds:g} s per step (CPU generator oracle/synth_cpu.hpp, "
+                                   f"{gen_s:.1f} s untimed), one receiver per stream, {cores} threads"},
         "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "wall_s": round(wall, 2), "messages_per_step": int(nm.sum()),
+        "wall_s": round(wall, 2), "headers_decoded_per_step": n_som,
+        "native_so_loaded": sorted({os.path.relpath(l.split()[-1], ROOT) for l in open("/proc/self/maps")
+                                    if l.rstrip().endswith(".so") and l.split()[-1].startswith(ROOT)}),
     }
     print(json.dumps(line))
     return 0

@@ -1,4 +1,4 @@
-//! Raw bindings to include/same_engine.h (ABI version 1).  Field order and types match the C header exactly.
+//! Raw bindings to include/same_engine.h (ABI version 2).  Field order and types match the C header exactly.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
@@ -57,6 +57,12 @@ pub struct same_engine {
     _private: [u8; 0],
 }
 
+/// Opaque handle: one batch sharded over several devices (one engine + one host thread per device).
+#[repr(C)]
+pub struct same_multi {
+    _private: [u8; 0],
+}
+
 /// Opaque copy of the resident state of all streams (`SameReceiver: Clone`, receiver.rs:70).
 #[repr(C)]
 pub struct same_snapshot {
@@ -105,13 +111,20 @@ extern "C" {
     pub fn same_engine_reset(e: *mut same_engine, stream_ids: *const u32, n: u32) -> c_int;
     pub fn same_engine_submit_s16(e: *mut same_engine, samples: *const i16, total_samples: u64, offsets: *const u64, lengths: *const u32) -> c_int;
     pub fn same_engine_submit_s16_2d(e: *mut same_engine, samples: *const i16, row_stride: u64, col_start: u64, n_cols: u32) -> c_int;
+    // the reference's own item type: iter_events<I: IntoIterator<Item = f32>> (receiver.rs:119-130)
+    pub fn same_engine_submit_f32(e: *mut same_engine, samples: *const f32, total_samples: u64, offsets: *const u64, lengths: *const u32) -> c_int;
+    pub fn same_engine_submit_f32_device(e: *mut same_engine, d_samples: *const f32, total_samples: u64, offsets: *const u64,
+                                         lengths: *const u32) -> c_int;
     pub fn same_engine_submit_zeros(e: *mut same_engine, lengths: *const u32) -> c_int;
+    pub fn same_engine_lost_events(e: *mut same_engine, events_lost: *mut u64, payloads_lost: *mut u64) -> c_int;
     pub fn same_engine_sync(e: *mut same_engine) -> c_int;
     pub fn same_engine_pending(e: *mut same_engine, n_events: *mut usize, n_payload: *mut usize) -> c_int;
     pub fn same_engine_drain_events(e: *mut same_engine, events: *mut same_event, events_cap: usize, n_events: *mut usize,
                                     payload: *mut u8, payload_cap: usize, n_payload: *mut usize) -> c_int;
     pub fn same_host_alloc(bytes: usize) -> *mut c_void;
     pub fn same_host_free(p: *mut c_void);
+    pub fn same_h2d_probe(device: c_int, host: *const c_void, row_stride_bytes: usize, width_bytes: usize, rows: usize, reps: c_int,
+                          elapsed_ms: *mut f32) -> c_int;
     // samples already on the device (the engine's own corpus generator, or another CUDA producer)
     pub fn same_engine_submit_s16_device(e: *mut same_engine, d_samples: *const i16, total_samples: u64, offsets: *const u64,
                                          lengths: *const u32) -> c_int;
@@ -125,10 +138,30 @@ extern "C" {
     pub fn same_engine_enable_soft_trace(e: *mut same_engine, cap_per_stream: u32) -> c_int;
     pub fn same_engine_read_soft_trace(e: *mut same_engine, stream: u32, out: *mut same_soft_symbol, cap: usize, n: *mut usize) -> c_int;
     pub fn same_engine_set_option(e: *mut same_engine, key: *const c_char, value: c_int) -> c_int;
+    pub fn same_engine_get_option(e: *mut same_engine, key: *const c_char, value: *mut c_int) -> c_int;
     pub fn same_engine_last_timing(e: *mut same_engine, h2d_ms: *mut f32, kernel_ms: *mut f32) -> c_int;
     pub fn same_engine_launch_count(e: *const same_engine) -> u64;
     pub fn same_engine_timer_start(e: *mut same_engine) -> c_int;
     pub fn same_engine_timer_stop(e: *mut same_engine, elapsed_ms: *mut f32) -> c_int;
     pub fn same_engine_get_derived(e: *const same_engine, d: *mut same_derived, mark_re_im: *mut f32, space_re_im: *mut f32,
                                    cap_taps: usize) -> c_int;
+    // one batch over several devices: one host thread + one engine per device inside the library
+    pub fn same_multi_create(cfg: *const same_config, devices: *const c_int, n_devices: u32, n_streams: u32,
+                             out: *mut *mut same_multi) -> c_int;
+    pub fn same_multi_destroy(m: *mut same_multi);
+    pub fn same_multi_last_error(m: *const same_multi) -> *const c_char;
+    pub fn same_multi_num_shards(m: *const same_multi) -> u32;
+    pub fn same_multi_num_streams(m: *const same_multi) -> u32;
+    pub fn same_multi_shard_info(m: *const same_multi, shard: u32, device: *mut c_int, first_stream: *mut u32, n_streams: *mut u32) -> c_int;
+    pub fn same_multi_engine(m: *mut same_multi, shard: u32) -> *mut same_engine;
+    pub fn same_multi_submit_s16(m: *mut same_multi, samples: *const i16, total_samples: u64, offsets: *const u64, lengths: *const u32) -> c_int;
+    pub fn same_multi_submit_f32(m: *mut same_multi, samples: *const f32, total_samples: u64, offsets: *const u64, lengths: *const u32) -> c_int;
+    pub fn same_multi_submit_s16_2d(m: *mut same_multi, samples: *const i16, row_stride: u64, col_start: u64, n_cols: u32) -> c_int;
+    pub fn same_multi_submit_zeros(m: *mut same_multi, lengths: *const u32) -> c_int;
+    pub fn same_multi_sync(m: *mut same_multi) -> c_int;
+    pub fn same_multi_reset(m: *mut same_multi) -> c_int;
+    pub fn same_multi_input_sample_counters(m: *mut same_multi, out: *mut u64) -> c_int;
+    pub fn same_multi_pending(m: *mut same_multi, n_events: *mut usize, n_payload: *mut usize) -> c_int;
+    pub fn same_multi_drain_events(m: *mut same_multi, events: *mut same_event, events_cap: usize, n_events: *mut usize,
+                                   payload: *mut u8, payload_cap: usize, n_payload: *mut usize) -> c_int;
 }

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SAME_ABI_VERSION 1u
+#define SAME_ABI_VERSION 2u
 
 /* Status codes (the reference is infallible on this path — receiver.rs:434-436 `expect`, codesquelch.rs:230 asserts —
  * so every error here is an engine/resource error, never a decode error; decode errors are event values). */
@@ -34,7 +34,9 @@ enum same_status {
   SAME_ERR_INVALID_CONFIG = 2, /* a configuration the reference would panic on (e.g. DC length 0) or beyond engine limits */
   SAME_ERR_NO_DEVICE = 3,      /* no usable CUDA device / device index out of range */
   SAME_ERR_CUDA = 4,           /* CUDA runtime error; see same_engine_last_error */
-  SAME_ERR_EVENT_OVERFLOW = 5, /* event or payload arena too small for one submit; raise same_engine_set_event_capacity */
+  SAME_ERR_EVENT_OVERFLOW = 5, /* event or payload arena too small for what was produced between two syncs: the events
+                                  that fitted are still drainable and self-consistent, the rest are lost (counted by
+                                  same_engine_lost_events); raise same_engine_set_event_capacity or sync more often */
   SAME_ERR_BUSY = 6            /* call not allowed while a submit is in flight (sync first) */
 };
 
@@ -86,6 +88,7 @@ enum same_event_kind {
 #define SAME_EV_FLAG_TRUNCATED 1u /* burst longer than the engine's burst buffer (framing.rs:152-162 has no cap);
                                      the first SAME_BURST_CAP bytes are kept — the Assembler only uses 268 (assembler.rs:169) */
 #define SAME_BURST_CAP 1024u
+#define SAME_EV_FLAG_PAYLOAD_LOST 2u /* the payload arena was full: the event is reported with data_len == 0 */
 
 /* == SameReceiverEvent {what, input_sample_counter} (output.rs:24-27) plus the stream it belongs to. */
 typedef struct same_event {
@@ -135,9 +138,14 @@ int same_engine_snapshot(same_engine* e, same_snapshot** out);
 int same_engine_restore(same_engine* e, const same_snapshot* snap);
 void same_snapshot_free(same_snapshot* snap);
 
-/* Capacity of the per-submit event arena (events) and payload arena (bytes).  Defaults: 64 events and 4 KiB per stream,
- * at least 65536 events / 4 MiB. */
+/* Capacity of the device event arena (events) and payload arena (bytes).  The arenas fill from one same_engine_sync
+ * (or any call that implies it) to the next — NOT per submit: a long run of unsynced submits accumulates.  Defaults:
+ * 64 events and 4 KiB per stream, at least 65536 events / 4 MiB (a SAME stream produces ~30 events per minute).
+ * On overflow sync returns SAME_ERR_EVENT_OVERFLOW once; events beyond the capacity are dropped and counted, events
+ * whose payload did not fit are delivered with data_len 0 and SAME_EV_FLAG_PAYLOAD_LOST.  Implies sync. */
 int same_engine_set_event_capacity(same_engine* e, size_t max_events, size_t max_payload_bytes);
+/* Events dropped / payloads dropped because an arena was full, since create (cumulative). */
+int same_engine_lost_events(same_engine* e, uint64_t* events_lost, uint64_t* payloads_lost);
 
 /* Feed audio: == iter_events(input) driven to exhaustion for every stream (receiver.rs:119-130, 233-274), batched.
  * Stream i consumes samples[offsets[i] .. offsets[i]+lengths[i]) as `sa as f32` (crates/samedec/src/app.rs:112).
@@ -154,6 +162,15 @@ int same_engine_submit_s16_2d(same_engine* e, const int16_t* samples, uint64_t r
                               uint32_t n_cols);
 /* Same, but `d_samples` already lives in this device's memory (no copy). */
 int same_engine_submit_s16_device(same_engine* e, const int16_t* d_samples, uint64_t total_samples,
+                                  const uint64_t* offsets, const uint32_t* lengths);
+/* The reference's own sample type: iter_events<I: IntoIterator<Item = f32>> (receiver.rs:119-130; lib.rs:78-79 documents
+ * f32 PCM at any scale — the AGC normalises).  Arbitrary f32 samples (e.g. normalised to [-1, 1]) take the literal f32
+ * DC-blocker recursion (dcblock.rs:45-49,104-108) of the rate-generic kernel: the integer-exact fast path only holds
+ * for integer-valued input.  After the first f32 submit an engine stays on the generic kernel until
+ * same_engine_reset(all).  Host and device variants as for s16. */
+int same_engine_submit_f32(same_engine* e, const float* samples, uint64_t total_samples, const uint64_t* offsets,
+                           const uint32_t* lengths);
+int same_engine_submit_f32_device(same_engine* e, const float* d_samples, uint64_t total_samples,
                                   const uint64_t* offsets, const uint32_t* lengths);
 /* Feed lengths[i] zero samples to stream i: the body of SameReceiver::flush (receiver.rs:216-224) without its early
  * return; the host layer applies samedec's repeat-until-quiet rule (app.rs:71-74,118). */
@@ -174,15 +191,19 @@ int same_engine_drain_events(same_engine* e, same_event* events, size_t events_c
 int same_engine_enable_soft_trace(same_engine* e, uint32_t cap_per_stream);
 int same_engine_read_soft_trace(same_engine* e, uint32_t stream, same_soft_symbol* out, size_t cap, size_t* n);
 
-/* Engine options (diagnostic; every setting must produce identical results, the tests cross-check them).
- *   "force_generic"   0 engine picks the kernel from the batch size (default); 1 rate-generic kernel even where the
+/* Engine options (diagnostic; every setting must produce identical results, the tests cross-check them).  The library
+ * reads no environment variables: this call is the only way to override the measured kernel policy.
+ *   "kernel"          0 engine picks the kernel from the batch size (default); 1 rate-generic kernel even where the
  *                     22050 Hz fast kernels apply; 2 single-warp fast kernel; 3 four-warp pipelined kernel;
- *                     4 three-warp kernel
+ *                     4 three-warp kernel.  ("force_generic" is the old name of the same option.)
  *   "lanes_per_warp"  streams per warp of the fast kernels (1, 2, 4, 8, 16, 32)
  *   "device_sort"     1 (default): big batches of events are put into per-stream order on the device before the
  *                     read-back; 0: always on the host
  * Implies sync. */
 int same_engine_set_option(same_engine* e, const char* key, int value);
+/* Reads an option back; additionally "kernel_selected": the kernel the next s16 submit will launch (1 generic,
+ * 2 single-warp, 3 pipelined, 4 three-warp) — the policy result for this batch size unless "kernel" overrides it. */
+int same_engine_get_option(same_engine* e, const char* key, int* value);
 
 /* Timing of the last completed submit, measured with CUDA events on the engine's stream: host->device copy and
  * receiver kernel, in milliseconds; kernel launch count since create (for bench.py's gpu_launches). */
@@ -195,9 +216,15 @@ int same_engine_timer_stop(same_engine* e, float* elapsed_ms);
 /* cudaStream_t of the engine (as void*), so callers can order their own device work (e.g. a generator) before submit. */
 void* same_engine_cuda_stream(same_engine* e);
 
-/* Pinned host memory for sample buffers. */
+/* Pinned host memory for sample buffers (pinned for every device of the process). */
 void* same_host_alloc(size_t bytes);
 void same_host_free(void* p);
+/* Measurement aid: the bare host->device copy ceiling of this process on `device` — `reps` strided copies of `rows`
+ * rows of `width_bytes` (source pitch `row_stride_bytes`; width == pitch makes it one flat copy) from pinned `host`
+ * into a scratch device buffer, no kernel, timed with CUDA events.  bench.py runs it on every rank at once to get the
+ * box's aggregate pinned H2D rate that the end-to-end numbers are bounded by. */
+int same_h2d_probe(int device, const void* host, size_t row_stride_bytes, size_t width_bytes, size_t rows, int reps,
+                   float* elapsed_ms);
 
 /* Derived constants as the engine computed them on the host (receiver.rs:502-560), for parity tests. */
 typedef struct same_derived {
@@ -208,6 +235,40 @@ typedef struct same_derived {
 int same_engine_get_derived(const same_engine* e, same_derived* d, float* mark_re_im, float* space_re_im, size_t cap_taps);
 
 uint32_t same_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Several devices in one process (north_star: "streams shard naturally across the 8 GPUs of one box, with one host
+ * thread and CUDA stream per device ... no NCCL").  same_multi owns one engine and one host thread per entry of
+ * `devices` (a device may be listed more than once); shard i holds the contiguous global stream range
+ * [n_streams*i/n_devices, n_streams*(i+1)/n_devices).  Every call fans out to the shards' threads and returns when all
+ * of them have enqueued (submit) or finished (sync, drain).  Semantics per stream are those of the single-device calls
+ * above; events come back with GLOBAL stream ids, sorted by (stream, order of occurrence).  This is what a Rust
+ * iter_messages_batched over a whole box calls (bindings/rust/src/batched.rs).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct same_multi same_multi;
+int same_multi_create(const same_config* cfg, const int* devices, uint32_t n_devices, uint32_t n_streams, same_multi** out);
+void same_multi_destroy(same_multi* m);
+const char* same_multi_last_error(const same_multi* m);
+uint32_t same_multi_num_shards(const same_multi* m);
+uint32_t same_multi_num_streams(const same_multi* m);
+int same_multi_shard_info(const same_multi* m, uint32_t shard, int* device, uint32_t* first_stream, uint32_t* n_streams);
+/* The engine of one shard, for per-device settings and timers (same_engine_set_option, same_engine_timer_*). */
+same_engine* same_multi_engine(same_multi* m, uint32_t shard);
+/* offsets/lengths have n_streams (global) entries; each device copies only the span of `samples` its streams touch. */
+int same_multi_submit_s16(same_multi* m, const int16_t* samples, uint64_t total_samples, const uint64_t* offsets,
+                          const uint32_t* lengths);
+int same_multi_submit_f32(same_multi* m, const float* samples, uint64_t total_samples, const uint64_t* offsets,
+                          const uint32_t* lengths);
+/* HOST matrix samples[n_streams][row_stride]: device i takes its own rows, columns [col_start, col_start + n_cols). */
+int same_multi_submit_s16_2d(same_multi* m, const int16_t* samples, uint64_t row_stride, uint64_t col_start,
+                             uint32_t n_cols);
+int same_multi_submit_zeros(same_multi* m, const uint32_t* lengths);
+int same_multi_sync(same_multi* m);
+int same_multi_reset(same_multi* m);
+int same_multi_input_sample_counters(same_multi* m, uint64_t* out);
+int same_multi_pending(same_multi* m, size_t* n_events, size_t* n_payload_bytes);
+int same_multi_drain_events(same_multi* m, same_event* events, size_t events_cap, size_t* n_events, uint8_t* payload,
+                            size_t payload_cap, size_t* n_payload);
 
 #ifdef __cplusplus
 }

@@ -153,6 +153,15 @@ class SameBatchReceiver {
     ck(same_engine_sync(e_));
     return drain_by_stream();
   }
+  // the reference's own item type: iter_events<I: IntoIterator<Item = f32>> (receiver.rs:119-130), any scale
+  std::vector<std::vector<SameReceiverEvent>> process(const std::vector<std::vector<float>>& chunks) {
+    if (chunks.size() != n_) throw std::invalid_argument("one chunk per stream expected");
+    std::vector<float> flat; std::vector<uint64_t> off(n_); std::vector<uint32_t> len(n_);
+    for (uint32_t i = 0; i < n_; ++i) { off[i] = flat.size(); len[i] = (uint32_t)chunks[i].size(); flat.insert(flat.end(), chunks[i].begin(), chunks[i].end()); }
+    ck(same_engine_submit_f32(e_, flat.data(), flat.size(), off.data(), len.data()));
+    ck(same_engine_sync(e_));
+    return drain_by_stream();
+  }
   std::vector<std::vector<SameReceiverEvent>> process_zeros(const std::vector<uint32_t>& lengths) {
     ck(same_engine_submit_zeros(e_, lengths.data())); ck(same_engine_sync(e_)); return drain_by_stream();
   }
@@ -227,10 +236,19 @@ class SameReceiver {
   uint64_t input_sample_counter() { return b_.input_sample_counters()[0]; }
   void reset() { b_.reset(); }
   std::vector<SameReceiverEvent> iter_events(const std::vector<int16_t>& samples) {                                               // receiver.rs:119-130
-    auto evs = b_.process({samples});
+    auto evs = b_.process(std::vector<std::vector<int16_t>>{samples});
+    return std::move(evs[0]);
+  }
+  std::vector<SameReceiverEvent> iter_events(const std::vector<float>& samples) {                                                 // receiver.rs:119-130 (f32 items)
+    auto evs = b_.process(std::vector<std::vector<float>>{samples});
     return std::move(evs[0]);
   }
   std::vector<Message> iter_messages(const std::vector<int16_t>& samples) {                                                        // receiver.rs:155-161
+    std::vector<Message> out;
+    for (auto& e : iter_events(samples)) if (auto m = e.message_ok()) out.push_back(*m);
+    return out;
+  }
+  std::vector<Message> iter_messages(const std::vector<float>& samples) {
     std::vector<Message> out;
     for (auto& e : iter_events(samples)) if (auto m = e.message_ok()) out.push_back(*m);
     return out;

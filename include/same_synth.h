@@ -21,11 +21,12 @@ typedef struct same_synth_burst {
   uint32_t n_bytes;      /* preamble + payload */
 } same_synth_burst;
 
-/* Writes n_samples s16 samples for each of n_streams streams to d_out[stream * stride + n] (device memory on
- * `device`).  burst_begin has n_streams+1 entries (CSR into `bursts`).  All table pointers are HOST memory.
+/* Writes samples [first_sample, first_sample + n_samples) of each of n_streams streams to d_out[stream * stride + k],
+ * k = 0 .. n_samples-1 (device memory on `device`).  first_sample must be a multiple of 8; a stream generated in
+ * several windows is bit-identical to the same stream generated at once (time-chunked config 4, 24 h config 5).  burst_begin has n_streams+1 entries (CSR into `bursts`).  All table pointers are HOST memory.
  * Returns 0 or a CUDA error code; `err_text` (>= 256 bytes, may be NULL) receives the message. */
-int same_synth_generate(int device, int16_t* d_out, uint32_t n_streams, uint64_t stride, uint32_t n_samples,
-                        uint32_t rate, const uint32_t* burst_begin, const same_synth_burst* bursts, uint32_t n_bursts,
+int same_synth_generate(int device, int16_t* d_out, uint32_t n_streams, uint64_t stride, uint64_t first_sample,
+                        uint32_t n_samples, uint32_t rate, const uint32_t* burst_begin, const same_synth_burst* bursts, uint32_t n_bursts,
                         const uint8_t* bytes, uint64_t n_bytes_total, const float* freq_offset_hz,
                         const uint32_t* seeds, float amplitude, float noise_sigma, char* err_text);
 

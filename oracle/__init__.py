@@ -8,6 +8,9 @@ from .pyoracle import (  # noqa: F401
     OracleConfig,
     OracleEvent,
     build_oracle,
+    decode_batch_events,
+    synth_cpu,
+    BATCH_EVENT_DTYPE,
     load_golden_recording,
     GOLDEN_DIR,
     EV_NAMES,

@@ -93,7 +93,7 @@ def build_oracle(force=False):
     so = os.path.join(HERE, "_build", "liboracle.so")
     if force or not os.path.exists(so) or any(
         os.path.getmtime(os.path.join(HERE, f)) > os.path.getmtime(so)
-        for f in ("same_oracle.hpp", "same_oracle_capi.cpp")
+        for f in ("same_oracle.hpp", "same_oracle_capi.cpp", "synth_cpu.hpp")
     ):
         subprocess.run(["make", "-C", HERE, "all"], check=True, capture_output=True)
     return so
@@ -125,6 +125,19 @@ def _lib():
         lib.oracle_decode_batch.restype = C.c_double
         lib.oracle_decode_batch.argtypes = [C.POINTER(OracleConfig), C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                             C.c_int, C.c_void_p, C.c_void_p]
+        lib.oracle_decode_batch_events.restype = C.c_void_p
+        lib.oracle_decode_batch_events.argtypes = [C.POINTER(OracleConfig), C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                                   C.c_void_p, C.c_int, C.c_int]
+        lib.oracle_batch_num_events.restype = C.c_size_t
+        lib.oracle_batch_num_events.argtypes = [C.c_void_p]
+        lib.oracle_batch_payload_bytes.restype = C.c_size_t
+        lib.oracle_batch_payload_bytes.argtypes = [C.c_void_p]
+        lib.oracle_batch_seconds.restype = C.c_double
+        lib.oracle_batch_seconds.argtypes = [C.c_void_p]
+        lib.oracle_batch_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.oracle_batch_free.argtypes = [C.c_void_p]
+        lib.oracle_synth_generate.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int]
         _LIB = lib
     return _LIB
 
@@ -220,6 +233,62 @@ class Oracle:
         secs = _lib().oracle_decode_batch(C.byref(cfg), a.ctypes.data, a.shape[0], a.shape[1], a.shape[1],
                                           int(n_threads), nb.ctypes.data, nm.ctypes.data)
         return secs, nb, nm
+
+
+# same layout as include/same_engine.h:same_event (and sameold_b200.SameBatchReceiver.EVENT_DTYPE)
+BATCH_EVENT_DTYPE = np.dtype([("stream", "<u4"), ("seq", "<u4"), ("sample", "<u8"), ("symbol_count", "<u8"),
+                              ("kind", "<u4"), ("err", "<u4"), ("data_offset", "<u4"), ("data_len", "<u4"),
+                              ("parity_errors", "<u2"), ("voting_bytes", "<u2"), ("flags", "<u4")])
+
+
+def decode_batch_events(cfg, samples_2d, n_threads, lengths=None, flush=False):
+    """One oracle receiver per row of `samples_2d` (int16 [n_streams, stride]) on `n_threads` host threads; returns
+    (events, payload, seconds): a structured array in the engine's same_event layout sorted by (stream, occurrence;
+    seq counts from 0 per stream) and the concatenated payload bytes."""
+    a = samples_2d
+    assert a.dtype == np.int16 and a.ndim == 2 and a.strides[1] == 2
+    stride = a.strides[0] // 2
+    lens = None if lengths is None else np.ascontiguousarray(lengths, dtype=np.uint32)
+    h = _lib().oracle_decode_batch_events(C.byref(cfg), a.ctypes.data, a.shape[0], stride, a.shape[1],
+                                          None if lens is None else lens.ctypes.data, int(n_threads), 1 if flush else 0)
+    try:
+        ev = np.zeros(_lib().oracle_batch_num_events(h), BATCH_EVENT_DTYPE)
+        pay = np.zeros(max(_lib().oracle_batch_payload_bytes(h), 1), np.uint8)
+        _lib().oracle_batch_copy(h, ev.ctypes.data, pay.ctypes.data)
+        secs = _lib().oracle_batch_seconds(h)
+        return ev, pay[: _lib().oracle_batch_payload_bytes(h)], secs
+    finally:
+        _lib().oracle_batch_free(h)
+
+
+class _CpuBurst(C.Structure):
+    _fields_ = [("start_sample", C.c_double), ("byte_offset", C.c_uint32), ("n_bytes", C.c_uint32)]
+
+
+def synth_cpu(plans, n_samples, rate=22050, n_threads=1, amplitude=16384.0, noise_sigma=11585.0 / 10.0 ** 0.5):
+    """CPU rendering (oracle/synth_cpu.hpp, all host threads) of the corpus described by `plans` (objects with
+    burst_starts / burst_payloads / freq_offset_hz / seed, i.e. sameold_b200.synth.StreamPlan): int16 [len(plans),
+    n_samples].  Same signal model as the device generator; used by bench.py's reference arm so that arm loads no GPU
+    code."""
+    n = len(plans)
+    begin = np.zeros(n + 1, np.uint32)
+    bursts, blobs, off = [], [], 0
+    for i, p in enumerate(plans):
+        for s, b in zip(p.burst_starts, p.burst_payloads):
+            bursts.append((s, off, len(b)))
+            blobs.append(b)
+            off += len(b)
+        begin[i + 1] = len(bursts)
+    barr = (_CpuBurst * max(len(bursts), 1))()
+    for k, (s, o, l) in enumerate(bursts):
+        barr[k].start_sample, barr[k].byte_offset, barr[k].n_bytes = s, o, l
+    data = np.frombuffer(b"".join(blobs) or b"\0", dtype=np.uint8).copy()
+    foff = np.array([p.freq_offset_hz for p in plans], np.float32)
+    seeds = np.array([p.seed for p in plans], np.uint32)
+    out = np.empty((n, n_samples), np.int16)
+    _lib().oracle_synth_generate(out.ctypes.data, n, n_samples, n_samples, rate, begin.ctypes.data, barr, data.ctypes.data,
+                                 off, foff.ctypes.data, seeds.ctypes.data, amplitude, noise_sigma, int(n_threads))
+    return out
 
 
 def load_golden_recording(name):

@@ -1,6 +1,7 @@
 // same_oracle_capi.cpp — C ABI over the CPU oracle (TEST INFRASTRUCTURE ONLY; see same_oracle.hpp).
 // Loaded with ctypes by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
 #include "same_oracle.hpp"
+#include "synth_cpu.hpp"
 
 #include <atomic>
 #include <chrono>
@@ -200,6 +201,126 @@ double oracle_decode_batch(const oracle_config* c, const int16_t* samples, size_
   for (auto& x : th) x.join();
   auto t1 = std::chrono::steady_clock::now();
   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// ---- batch decode with the events handed back (full-size parity tests: every stream of config 3 / sampled streams of
+// config 4 against the engine).  Records use the engine's same_event layout (include/same_engine.h) so that the test
+// compares whole arrays: stream, seq (per-stream occurrence index), input_sample_counter, symbol_count, kind, err,
+// data_offset, data_len, parity_errors, voting_bytes, flags; burst payloads are capped at 1024 bytes with flag 1 set,
+// as the engine's burst buffer does (data_len keeps the true length).
+typedef struct oracle_batch_event {
+  uint32_t stream, seq;
+  uint64_t input_sample_counter, symbol_count;
+  uint32_t kind, err, data_offset, data_len;
+  uint16_t parity_errors, voting_bytes;
+  uint32_t flags;
+} oracle_batch_event;
+
+struct OracleBatch {
+  std::vector<oracle_batch_event> ev;
+  std::vector<uint8_t> payload;
+  double seconds = 0.0;
+};
+
+// `lengths` may be NULL (every stream has `len` samples).  `flush` != 0 applies samedec's EOF flush rule per stream.
+void* oracle_decode_batch_events(const oracle_config* c, const int16_t* samples, size_t n_streams, size_t stride, size_t len,
+                                 const uint32_t* lengths, int n_threads, int flush) {
+  Config k = to_config(c);
+  if (n_threads < 1) n_threads = 1;
+  std::vector<std::vector<oracle_batch_event>> evs(n_streams);
+  std::vector<std::vector<uint8_t>> pays(n_streams);
+  std::atomic<size_t> next{0};
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> th;
+  for (int t = 0; t < n_threads; ++t) {
+    th.emplace_back([&]() {
+      std::vector<Event> ev;
+      while (true) {
+        size_t s = next.fetch_add(1);
+        if (s >= n_streams) break;
+        SameReceiver rx(k);
+        ev.clear();
+        const int16_t* p = samples + s * stride;
+        const size_t n = lengths ? lengths[s] : len;
+        for (size_t i = 0; i < n; ++i) rx.process_sample((float)p[i], ev);
+        if (flush) samedec_eof_flush(rx, ev);
+        uint32_t seq = 0;
+        for (auto& e : ev) {
+          oracle_batch_event r;
+          memset(&r, 0, sizeof r);
+          r.stream = (uint32_t)s; r.seq = seq++;
+          r.input_sample_counter = e.input_sample_counter; r.symbol_count = e.symbol_count;
+          if (!e.is_transport) r.kind = (uint32_t)e.link.kind;
+          else if (e.transport.kind == TransportKind::Idle) r.kind = OR_EV_TR_IDLE;
+          else if (e.transport.kind == TransportKind::Assembling) r.kind = OR_EV_TR_ASSEMBLING;
+          else if (!e.transport.res.ok) { r.kind = OR_EV_TR_MSG_ERR; r.err = (uint32_t)e.transport.res.err; }
+          else if (e.transport.res.msg.is_som) {
+            r.kind = OR_EV_TR_MSG_SOM;
+            r.parity_errors = (uint16_t)e.transport.res.msg.parity_error_count;
+            r.voting_bytes = (uint16_t)e.transport.res.msg.voting_byte_count;
+          } else r.kind = OR_EV_TR_MSG_EOM;
+          std::string tmp;
+          const std::string& txt = ev_text(e, tmp);
+          r.data_len = (uint32_t)txt.size();
+          size_t keep = txt.size();
+          if (r.kind == OR_EV_LINK_BURST && keep > 1024) { keep = 1024; r.flags = 1; }
+          r.data_offset = (uint32_t)pays[s].size();
+          pays[s].insert(pays[s].end(), txt.begin(), txt.begin() + keep);
+          evs[s].push_back(r);
+        }
+      }
+    });
+  }
+  for (auto& x : th) x.join();
+  auto t1 = std::chrono::steady_clock::now();
+  auto* out = new OracleBatch();
+  out->seconds = std::chrono::duration<double>(t1 - t0).count();
+  for (size_t s = 0; s < n_streams; ++s) {
+    const uint32_t base = (uint32_t)out->payload.size();
+    for (auto r : evs[s]) { r.data_offset += base; out->ev.push_back(r); }
+    out->payload.insert(out->payload.end(), pays[s].begin(), pays[s].end());
+  }
+  return out;
+}
+size_t oracle_batch_num_events(void* h) { return ((OracleBatch*)h)->ev.size(); }
+size_t oracle_batch_payload_bytes(void* h) { return ((OracleBatch*)h)->payload.size(); }
+double oracle_batch_seconds(void* h) { return ((OracleBatch*)h)->seconds; }
+void oracle_batch_copy(void* h, oracle_batch_event* events, uint8_t* payload) {
+  auto* b = (OracleBatch*)h;
+  if (events && !b->ev.empty()) memcpy(events, b->ev.data(), b->ev.size() * sizeof(oracle_batch_event));
+  if (payload && !b->payload.empty()) memcpy(payload, b->payload.data(), b->payload.size());
+}
+void oracle_batch_free(void* h) { delete (OracleBatch*)h; }
+
+// CPU corpus generator for bench.py's reference arm (see synth_cpu.hpp): out[s * stride + n], n < n_samples, for
+// n_streams streams on n_threads host threads.  burst_begin has n_streams + 1 entries (CSR into `bursts`).
+void oracle_synth_generate(int16_t* out, size_t n_streams, size_t stride, size_t n_samples, uint32_t rate,
+                           const uint32_t* burst_begin, const synth_cpu::Burst* bursts, const uint8_t* bytes,
+                           size_t n_bytes_total, const float* freq_offset_hz, const uint32_t* seeds, float amplitude,
+                           float noise_sigma, int n_threads) {
+  std::vector<uint16_t> cum(n_bytes_total ? n_bytes_total : 1);
+  for (uint32_t b = 0; b < burst_begin[n_streams]; ++b) {
+    uint32_t acc = 0;
+    for (uint32_t i = 0; i < bursts[b].n_bytes; ++i) {
+      cum[bursts[b].byte_offset + i] = (uint16_t)acc;
+      acc += (uint32_t)__builtin_popcount(bytes[bursts[b].byte_offset + i]);
+    }
+  }
+  if (n_threads < 1) n_threads = 1;
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> th;
+  for (int t = 0; t < n_threads; ++t) {
+    th.emplace_back([&]() {
+      while (true) {
+        const size_t s = next.fetch_add(1);
+        if (s >= n_streams) break;
+        synth_cpu::render_stream(out + s * stride, n_samples, (double)rate, bursts + burst_begin[s],
+                                 burst_begin[s + 1] - burst_begin[s], bytes, cum.data(), freq_offset_hz[s], seeds[s],
+                                 amplitude, noise_sigma);
+      }
+    });
+  }
+  for (auto& x : th) x.join();
 }
 
 }  // extern "C"

@@ -9,6 +9,7 @@ from .receiver import (  # noqa: F401
     Message,
     SameBatchReceiver,
     SameEngineError,
+    SameMultiReceiver,
     SameReceiver,
     SameReceiverBuilder,
     SameReceiverEvent,

@@ -76,13 +76,17 @@ API = {
     "same_engine_submit_s16": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
     "same_engine_submit_s16_2d": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint32]),
     "same_engine_submit_s16_device": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
+    "same_engine_submit_f32": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
+    "same_engine_submit_f32_device": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
     "same_engine_submit_zeros": (C.c_int, [_P, _P]),
+    "same_engine_lost_events": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "same_engine_sync": (C.c_int, [_P]),
     "same_engine_pending": (C.c_int, [_P, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "same_engine_drain_events": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t), _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "same_engine_enable_soft_trace": (C.c_int, [_P, C.c_uint32]),
     "same_engine_read_soft_trace": (C.c_int, [_P, C.c_uint32, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "same_engine_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
+    "same_engine_get_option": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int)]),
     "same_engine_last_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "same_engine_launch_count": (C.c_uint64, [_P]),
     "same_engine_timer_start": (C.c_int, [_P]),
@@ -90,9 +94,27 @@ API = {
     "same_engine_cuda_stream": (_P, [_P]),
     "same_host_alloc": (_P, [C.c_size_t]),
     "same_host_free": (None, [_P]),
+    "same_h2d_probe": (C.c_int, [C.c_int, _P, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_float)]),
     "same_engine_get_derived": (C.c_int, [_P, C.POINTER(SameDerived), _P, _P, C.c_size_t]),
+    # several devices in one process
+    "same_multi_create": (C.c_int, [C.POINTER(SameConfig), C.POINTER(C.c_int), C.c_uint32, C.c_uint32, C.POINTER(_P)]),
+    "same_multi_destroy": (None, [_P]),
+    "same_multi_last_error": (C.c_char_p, [_P]),
+    "same_multi_num_shards": (C.c_uint32, [_P]),
+    "same_multi_num_streams": (C.c_uint32, [_P]),
+    "same_multi_shard_info": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "same_multi_engine": (_P, [_P, C.c_uint32]),
+    "same_multi_submit_s16": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
+    "same_multi_submit_f32": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
+    "same_multi_submit_s16_2d": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint32]),
+    "same_multi_submit_zeros": (C.c_int, [_P, _P]),
+    "same_multi_sync": (C.c_int, [_P]),
+    "same_multi_reset": (C.c_int, [_P]),
+    "same_multi_input_sample_counters": (C.c_int, [_P, _P]),
+    "same_multi_pending": (C.c_int, [_P, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "same_multi_drain_events": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t), _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     # synthetic corpus generator (bench / test tooling, same library)
-    "same_synth_generate": (C.c_int, [C.c_int, _P, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, _P, _P, C.c_uint32,
+    "same_synth_generate": (C.c_int, [C.c_int, _P, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, _P, _P, C.c_uint32,
                                       _P, C.c_uint64, _P, _P, C.c_float, C.c_float, _P]),
 }
 

@@ -17,7 +17,7 @@
 #include "same_params.h"
 
 extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps, const SameTaps2* taps2, int force_generic,
-                                      uint32_t lanes_per_warp, const int16_t* d_samples,
+                                      uint32_t lanes_per_warp, const void* d_samples, int sample_fmt,
                                       const unsigned long long* d_offsets, const uint32_t* d_lengths,
                                       cudaStream_t stream);
 extern "C" cudaError_t same_launch_evsort(const same_event* d_events, uint32_t n, uint32_t n_streams, uint32_t* d_cnt,
@@ -64,7 +64,7 @@ size_t f32_as_usize(float x) {  // `as usize`: truncating, saturating, NaN -> 0
 }
 
 struct InputBuf {
-  int16_t* d = nullptr; size_t cap = 0;          // device samples
+  uint8_t* d = nullptr; size_t cap = 0;          // device samples (s16 or f32), capacity in bytes
   unsigned long long* d_off = nullptr; uint32_t* d_len = nullptr;
   cudaEvent_t copied = nullptr, consumed = nullptr;
   bool used = false;
@@ -83,6 +83,8 @@ struct same_engine {
   uint32_t lanes_per_warp = 32;   // streams per warp in the fast kernel (lane-sparse warps for small batches)
   int sm_count = 148;
   int kernel_auto = 0;            // fast-kernel flavour when force_generic == 0: 3 pipelined, 4 three-warp, 2 single-warp
+  bool saw_f32 = false;           // an f32 submit happened since create / reset(all): DC state may be non-integer -> generic kernel
+  uint64_t lost_events = 0, lost_payloads = 0;
   same_derived derived;
   cudaStream_t compute = nullptr, copy = nullptr;
   uint32_t* d_state = nullptr;
@@ -150,15 +152,16 @@ int collect(same_engine* e) {
   CK(e, cudaStreamSynchronize(e->compute));
   const size_t nev = e->h_counters[0], npay = e->h_counters[1];
   int rc = SAME_OK;
-  if (e->h_counters[2] != 0) {
-    char buf[128];
-    snprintf(buf, sizeof buf, "device watchdog tripped (code %u): producer/consumer hand-off stalled", e->h_counters[2]);
-    rc = fail(e, SAME_ERR_CUDA, buf);
-  }
-  if (nev > e->events_cap || npay > e->payload_cap) {
+  if (nev > e->events_cap || e->h_counters[2] != 0) {
+    // Events beyond the arena were dropped by the device; events whose payload did not fit were stored with
+    // data_len 0 + SAME_EV_FLAG_PAYLOAD_LOST (same_transport.cuh:emit_event_impl), so everything handed to the caller
+    // below stays self-consistent.  The stream state has advanced: what was dropped is lost, and counted.
+    const uint64_t ev_lost = nev > e->events_cap ? nev - e->events_cap : 0;
+    e->lost_events += ev_lost;
+    e->lost_payloads += e->h_counters[2];
     char buf[256];
-    snprintf(buf, sizeof buf, "event arena overflow: %zu events / %zu payload bytes produced, capacity %zu / %zu",
-             nev, npay, e->events_cap, e->payload_cap);
+    snprintf(buf, sizeof buf, "event arena overflow since the last sync: %llu events dropped (capacity %zu), %u payloads dropped "
+             "(capacity %zu bytes)", (unsigned long long)ev_lost, e->events_cap, e->h_counters[2], e->payload_cap);
     rc = fail(e, SAME_ERR_EVENT_OVERFLOW, buf);
   }
   const size_t cev = std::min(nev, e->events_cap), cpay = std::min(npay, e->payload_cap);
@@ -206,26 +209,34 @@ int collect(same_engine* e) {
         done += qn[pslot]; pslot ^= 1; --inflight;
       }
     }
-    for (size_t i = base_ev; i < base_ev + cev; ++i) e->pend_events[i].data_offset += (uint32_t)base_pay;
+    for (size_t i = base_ev; i < base_ev + cev; ++i) {
+      same_event& ev = e->pend_events[i];
+      const uint32_t stored = ev.kind == SAME_EV_LINK_BURST ? std::min<uint32_t>(ev.data_len, SAME_BURST_CAP) : ev.data_len;
+      if ((size_t)ev.data_offset + stored > cpay) {   // cannot happen with a sane device record: never hand out a bad offset
+        ev.data_offset = 0; ev.data_len = 0; ev.flags |= SAME_EV_FLAG_PAYLOAD_LOST;
+      }
+      ev.data_offset += (uint32_t)base_pay;
+    }
   }
   CK(e, cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(unsigned int), e->compute));
   return rc;
 }
 
-int ensure_input(same_engine* e, InputBuf& b, size_t samples) {
-  if (samples > b.cap) {
+int ensure_input(same_engine* e, InputBuf& b, size_t bytes) {
+  if (bytes > b.cap) {
     if (b.d) CK(e, cudaFree(b.d));
     b.d = nullptr; b.cap = 0;
-    size_t cap = samples + samples / 8 + 4096;
-    CK(e, cudaMalloc(&b.d, cap * sizeof(int16_t)));
+    size_t cap = bytes + bytes / 8 + 8192;
+    CK(e, cudaMalloc(&b.d, cap));
     b.cap = cap;
   }
   return SAME_OK;
 }
 
-struct Submit2D { uint64_t row_stride = 0, col_start = 0; uint32_t n_cols = 0; bool on = false; };
+struct Submit2D { uint64_t row_stride = 0, col_start = 0, dpitch = 0; uint32_t n_cols = 0; bool on = false; };
 
-int submit_common(same_engine* e, const int16_t* host_samples, const int16_t* dev_samples, uint64_t total,
+// sample_fmt: 0 = int16, 1 = float32
+int submit_common(same_engine* e, const void* host_samples, const void* dev_samples, int sample_fmt, uint64_t total,
                   const uint64_t* offsets, const uint32_t* lengths, bool zeros, Submit2D two_d = Submit2D()) {
   if (!e) return fail(nullptr, SAME_ERR_INVALID_ARG, "null engine");
   std::vector<uint64_t> off2d;
@@ -233,10 +244,13 @@ int submit_common(same_engine* e, const int16_t* host_samples, const int16_t* de
   if (two_d.on) {
     if (!host_samples) return fail(e, SAME_ERR_INVALID_ARG, "null argument");
     if (two_d.col_start + two_d.n_cols > two_d.row_stride) return fail(e, SAME_ERR_INVALID_ARG, "column range exceeds row_stride");
+    // device rows are packed at a pitch that is a multiple of 8 samples, so that every row starts 16-byte aligned and
+    // the fast kernels keep their 16-byte vector loads whatever n_cols is
+    two_d.dpitch = ((uint64_t)two_d.n_cols + 7u) & ~(uint64_t)7u;
     off2d.resize(e->n_streams); len2d.assign(e->n_streams, two_d.n_cols);
-    for (uint32_t i = 0; i < e->n_streams; ++i) off2d[i] = (uint64_t)i * two_d.n_cols;
+    for (uint32_t i = 0; i < e->n_streams; ++i) off2d[i] = (uint64_t)i * two_d.dpitch;
     offsets = off2d.data(); lengths = len2d.data();
-    total = (uint64_t)e->n_streams * two_d.n_cols;
+    total = (uint64_t)e->n_streams * two_d.dpitch;
   }
   if (!lengths || (!zeros && (!offsets || (!host_samples && !dev_samples && total))))
     return fail(e, SAME_ERR_INVALID_ARG, "null argument");
@@ -254,22 +268,24 @@ int submit_common(same_engine* e, const int16_t* host_samples, const int16_t* de
   // the copy stream may only overwrite this buffer after the kernel that last read it has finished
   if (b.used) CK(e, cudaStreamWaitEvent(e->copy, b.consumed, 0));
   e->timed_h2d = false;
-  const int16_t* d_src = nullptr;
+  const void* d_src = nullptr;
+  const size_t ssz = sample_fmt == 1 ? sizeof(float) : sizeof(int16_t);
+  if (sample_fmt == 1) e->saw_f32 = true;
   if (!zeros) {
     static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "offset type");
     CK(e, cudaMemcpyAsync(b.d_off, offsets, e->n_streams * sizeof(uint64_t), cudaMemcpyHostToDevice, e->copy));
   }
   CK(e, cudaMemcpyAsync(b.d_len, lengths, e->n_streams * sizeof(uint32_t), cudaMemcpyHostToDevice, e->copy));
   if (!zeros && host_samples) {
-    int rc = ensure_input(e, b, total);
+    int rc = ensure_input(e, b, total * ssz);
     if (rc) return rc;
     CK(e, cudaEventRecord(e->t_h2d0, e->copy));
     if (total && two_d.on)
-      CK(e, cudaMemcpy2DAsync(b.d, (size_t)two_d.n_cols * sizeof(int16_t), host_samples + two_d.col_start,
-                              (size_t)two_d.row_stride * sizeof(int16_t), (size_t)two_d.n_cols * sizeof(int16_t),
+      CK(e, cudaMemcpy2DAsync(b.d, (size_t)two_d.dpitch * ssz, static_cast<const uint8_t*>(host_samples) + two_d.col_start * ssz,
+                              (size_t)two_d.row_stride * ssz, (size_t)two_d.n_cols * ssz,
                               e->n_streams, cudaMemcpyHostToDevice, e->copy));
     else if (total)
-      CK(e, cudaMemcpyAsync(b.d, host_samples, total * sizeof(int16_t), cudaMemcpyHostToDevice, e->copy));
+      CK(e, cudaMemcpyAsync(b.d, host_samples, total * ssz, cudaMemcpyHostToDevice, e->copy));
     CK(e, cudaEventRecord(e->t_h2d1, e->copy));
     e->timed_h2d = true;
     d_src = b.d;
@@ -279,7 +295,9 @@ int submit_common(same_engine* e, const int16_t* host_samples, const int16_t* de
   CK(e, cudaEventRecord(b.copied, e->copy));
   CK(e, cudaStreamWaitEvent(e->compute, b.copied, 0));
   CK(e, cudaEventRecord(e->t_k0, e->compute));
-  CK(e, same_launch_rx(&e->p, &e->taps, &e->taps2, e->force_generic ? e->force_generic : e->kernel_auto, e->lanes_per_warp, d_src, b.d_off, b.d_len, e->compute));
+  // f32 input (now or earlier: the DC-blocker state may hold non-integers) needs the literal f32 recursion
+  const int kernel = e->saw_f32 ? 1 : (e->force_generic ? e->force_generic : e->kernel_auto);
+  CK(e, same_launch_rx(&e->p, &e->taps, &e->taps2, kernel, e->lanes_per_warp, d_src, sample_fmt, b.d_off, b.d_len, e->compute));
   CK(e, cudaEventRecord(e->t_k1, e->compute));
   CK(e, cudaEventRecord(b.consumed, e->compute));
   b.used = true;
@@ -388,7 +406,6 @@ int same_engine_create(const same_config* cfg_in, int device, uint32_t n_streams
     e->taps2.space[i] = make_float2(e->taps.space_re[i], e->taps.space_im[i]);
   }
   p.f_one = 1.0f; p.f_negzero = -0.0f;
-  if (const char* fg = getenv("SAME_FORCE_GENERIC")) e->force_generic = atoi(fg);
   {
     // Kernel / mapping policy for the 22050 Hz class (measured on B200, profiles/README.md):
     //  * up to 1 block per SM: four-warp pipelined kernel (producer / AGC / space filter / consumer), every warp on
@@ -399,20 +416,14 @@ int same_engine_create(const same_config* cfg_in, int device, uint32_t n_streams
     //    and helper warps would only compete for issue slots).
     //  Measured on B200 (20 s streams, ms per launch, pipelined / three-warp / single-warp): 4096 streams 24.0 / 24.9 /
     //  41.6; 8192: 36.8 / 29.1 / 42.4; 16384: 74.6 / 40.0 / 43.3; 65536: 228 / 158 / 116  (tools/matrix.sh).
-    // SAME_LANES_PER_WARP / option "lanes_per_warp" spread streams over more, lane-sparse warps (diagnostic).
+    // Option "lanes_per_warp" spreads streams over more, lane-sparse warps (diagnostic).  No environment variable is
+    // read here: same_engine_set_option is the only override.
     int sms = 148;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
     e->sm_count = sms;
     e->lanes_per_warp = 32;
     const uint32_t blocks32 = (n_streams + 31u) / 32u;
     e->kernel_auto = (blocks32 <= (uint32_t)sms) ? 3 : (blocks32 <= 4u * (uint32_t)sms) ? 4 : 2;
-    if (const char* lw = getenv("SAME_LANES_PER_WARP")) {
-      uint32_t v = (uint32_t)atoi(lw);
-      if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) e->lanes_per_warp = v;
-    }
-    if (const char* kv = getenv("SAME_KERNEL")) {   // diagnostic: ws | 2 (single warp) | pipe
-      e->kernel_auto = atoi(kv) == 2 ? 2 : (strcmp(kv, "pipe") == 0 || atoi(kv) == 3) ? 3 : 4;
-    }
   }
   p.spt = sps / 2.0f;                                                         // symsync.rs:146
   {
@@ -562,6 +573,7 @@ int same_engine_reset(same_engine* e, const uint32_t* ids, uint32_t n) {
     e->launches += 1;
     // SameReceiver::reset clears the event queue (receiver.rs:194)
     e->pend_events.clear(); e->pend_payload.clear();
+    e->saw_f32 = false;   // every DC-blocker window is zero again
   } else {
     for (uint32_t i = 0; i < n; ++i)
       if (ids[i] >= e->n_streams) return fail(e, SAME_ERR_INVALID_ARG, "stream id out of range");
@@ -580,9 +592,6 @@ int same_engine_reset(same_engine* e, const uint32_t* ids, uint32_t n) {
     e->pend_events.erase(std::remove_if(e->pend_events.begin(), e->pend_events.end(),
                                         [&](const same_event& ev) { return is_reset[ev.stream] != 0; }),
                          e->pend_events.end());
-  }
-  if (e->d_trace) {
-    // trace fill counters live in the state and were zeroed by the init kernel
   }
   CK(e, cudaStreamSynchronize(e->compute));
   return SAME_OK;
@@ -646,22 +655,40 @@ int same_engine_set_event_capacity(same_engine* e, size_t max_events, size_t max
 
 int same_engine_submit_s16(same_engine* e, const int16_t* samples, uint64_t total_samples, const uint64_t* offsets,
                            const uint32_t* lengths) {
-  return submit_common(e, samples, nullptr, total_samples, offsets, lengths, false);
+  return submit_common(e, samples, nullptr, 0, total_samples, offsets, lengths, false);
+}
+
+int same_engine_submit_f32(same_engine* e, const float* samples, uint64_t total_samples, const uint64_t* offsets,
+                           const uint32_t* lengths) {
+  return submit_common(e, samples, nullptr, 1, total_samples, offsets, lengths, false);
+}
+
+int same_engine_submit_f32_device(same_engine* e, const float* d_samples, uint64_t total_samples,
+                                  const uint64_t* offsets, const uint32_t* lengths) {
+  return submit_common(e, nullptr, d_samples, 1, total_samples, offsets, lengths, false);
+}
+
+int same_engine_lost_events(same_engine* e, uint64_t* events_lost, uint64_t* payloads_lost) {
+  if (!e) return fail(nullptr, SAME_ERR_INVALID_ARG, "null engine");
+  if (e->in_flight) { int rc = same_engine_sync(e); if (rc && rc != SAME_ERR_EVENT_OVERFLOW) return rc; }
+  if (events_lost) *events_lost = e->lost_events;
+  if (payloads_lost) *payloads_lost = e->lost_payloads;
+  return SAME_OK;
 }
 
 int same_engine_submit_s16_2d(same_engine* e, const int16_t* samples, uint64_t row_stride, uint64_t col_start,
                               uint32_t n_cols) {
   Submit2D t; t.row_stride = row_stride; t.col_start = col_start; t.n_cols = n_cols; t.on = true;
-  return submit_common(e, samples, nullptr, 0, nullptr, nullptr, false, t);
+  return submit_common(e, samples, nullptr, 0, 0, nullptr, nullptr, false, t);
 }
 
 int same_engine_submit_s16_device(same_engine* e, const int16_t* d_samples, uint64_t total_samples,
                                   const uint64_t* offsets, const uint32_t* lengths) {
-  return submit_common(e, nullptr, d_samples, total_samples, offsets, lengths, false);
+  return submit_common(e, nullptr, d_samples, 0, total_samples, offsets, lengths, false);
 }
 
 int same_engine_submit_zeros(same_engine* e, const uint32_t* lengths) {
-  return submit_common(e, nullptr, nullptr, 0, nullptr, lengths, true);
+  return submit_common(e, nullptr, nullptr, 0, 0, nullptr, lengths, true);
 }
 
 int same_engine_pending(same_engine* e, size_t* n_events, size_t* n_payload_bytes) {
@@ -747,12 +774,29 @@ int same_engine_set_option(same_engine* e, const char* key, int value) {
   if (!e || !key) return fail(e, SAME_ERR_INVALID_ARG, "null argument");
   int rc = same_engine_sync(e);
   if (rc) return rc;
-  if (strcmp(key, "force_generic") == 0) { e->force_generic = value; return SAME_OK; }
+  if (strcmp(key, "kernel") == 0 || strcmp(key, "force_generic") == 0) {
+    if (value < 0 || value > 4) return fail(e, SAME_ERR_INVALID_ARG, "kernel must be 0 (policy), 1 generic, 2 single-warp, 3 pipelined or 4 three-warp");
+    e->force_generic = value;
+    return SAME_OK;
+  }
   if (strcmp(key, "device_sort") == 0) { e->device_sort = value != 0; return SAME_OK; }
   if (strcmp(key, "lanes_per_warp") == 0) {
     if (!(value == 1 || value == 2 || value == 4 || value == 8 || value == 16 || value == 32))
       return fail(e, SAME_ERR_INVALID_ARG, "lanes_per_warp must be a power of two in 1..32");
     e->lanes_per_warp = (uint32_t)value;
+    return SAME_OK;
+  }
+  return fail(e, SAME_ERR_INVALID_ARG, std::string("unknown option ") + key);
+}
+
+int same_engine_get_option(same_engine* e, const char* key, int* value) {
+  if (!e || !key || !value) return fail(e, SAME_ERR_INVALID_ARG, "null argument");
+  if (strcmp(key, "kernel") == 0 || strcmp(key, "force_generic") == 0) { *value = e->force_generic; return SAME_OK; }
+  if (strcmp(key, "device_sort") == 0) { *value = e->device_sort; return SAME_OK; }
+  if (strcmp(key, "lanes_per_warp") == 0) { *value = (int)e->lanes_per_warp; return SAME_OK; }
+  if (strcmp(key, "kernel_selected") == 0) {
+    const bool fast_geometry = e->p.ntaps == 42 && e->p.dc_len == 16;
+    *value = (e->saw_f32 || !fast_geometry) ? 1 : (e->force_generic ? e->force_generic : e->kernel_auto);
     return SAME_OK;
   }
   return fail(e, SAME_ERR_INVALID_ARG, std::string("unknown option ") + key);
@@ -799,12 +843,37 @@ int same_engine_get_derived(const same_engine* e, same_derived* d, float* mark_r
 
 void* same_host_alloc(size_t bytes) {
   void* p = nullptr;
-  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {   // pinned for every device (same_multi)
     g_last_error = "cudaHostAlloc failed";
     return nullptr;
   }
   return p;
 }
 void same_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int same_h2d_probe(int device, const void* host, size_t row_stride_bytes, size_t width_bytes, size_t rows, int reps,
+                   float* elapsed_ms) {
+  if (!host || !elapsed_ms || !width_bytes || !rows || reps < 1 || width_bytes > row_stride_bytes)
+    return fail(nullptr, SAME_ERR_INVALID_ARG, "bad probe arguments");
+  cudaStream_t st = nullptr; cudaEvent_t a = nullptr, b = nullptr; void* d = nullptr;
+  cudaError_t err = cudaSetDevice(device);
+  if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  if (err == cudaSuccess) err = cudaEventCreate(&a);
+  if (err == cudaSuccess) err = cudaEventCreate(&b);
+  if (err == cudaSuccess) err = cudaMalloc(&d, width_bytes * rows);
+  if (err == cudaSuccess) err = cudaMemcpy2DAsync(d, width_bytes, host, row_stride_bytes, width_bytes, rows, cudaMemcpyHostToDevice, st);  // warm-up
+  if (err == cudaSuccess) err = cudaEventRecord(a, st);
+  for (int i = 0; i < reps && err == cudaSuccess; ++i)
+    err = cudaMemcpy2DAsync(d, width_bytes, host, row_stride_bytes, width_bytes, rows, cudaMemcpyHostToDevice, st);
+  if (err == cudaSuccess) err = cudaEventRecord(b, st);
+  if (err == cudaSuccess) err = cudaEventSynchronize(b);
+  if (err == cudaSuccess) err = cudaEventElapsedTime(elapsed_ms, a, b);
+  if (d) cudaFree(d);
+  if (a) cudaEventDestroy(a);
+  if (b) cudaEventDestroy(b);
+  if (st) cudaStreamDestroy(st);
+  if (err != cudaSuccess) return fail(nullptr, SAME_ERR_CUDA, std::string("h2d probe: ") + cudaGetErrorString(err));
+  return SAME_OK;
+}
 
 }  // extern "C"

@@ -37,10 +37,12 @@ namespace same_dev {
 // ----------------------------------------------------------------------------------------------------------------
 // Generic kernel.  RW = demod window ring slots (power of two >= ntaps); RD = DC ring slots (power of two >= dc_len)
 // ----------------------------------------------------------------------------------------------------------------
-template <int RW, int RD>
+// T = sample type at the boundary: int16_t (`sa as f32`, samedec app.rs:112) or float (the reference's own
+// iter_events item type, receiver.rs:119-130).
+template <int RW, int RD, typename T>
 __global__ void __launch_bounds__(32) same_rx_generic_kernel(const __grid_constant__ SameParams p,
                                                              const __grid_constant__ SameTaps taps,
-                                                             const int16_t* __restrict__ samples,
+                                                             const T* __restrict__ samples,
                                                              const unsigned long long* __restrict__ offsets,
                                                              const uint32_t* __restrict__ lengths) {
   extern __shared__ float smem[];
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(32) same_rx_generic_kernel(const __grid_consta
 
   const uint32_t len = valid ? lengths[s] : 0u;
   if (__all_sync(0xffffffffu, len == 0u)) return;
-  const int16_t* src = (samples != nullptr && valid) ? samples + offsets[s] : nullptr;
+  const T* src = (samples != nullptr && valid) ? samples + offsets[s] : nullptr;
 
   Lane a;
   lane_load(a, p, st, s);
@@ -1193,34 +1195,40 @@ __global__ void same_evsort_scatter(const same_event* __restrict__ ev, uint32_t 
 // Launchers (called from same_engine.cu)
 // ----------------------------------------------------------------------------------------------------------------
 extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps, const SameTaps2* taps2, int force_generic,
-                                      uint32_t lanes_per_warp, const int16_t* d_samples,
+                                      uint32_t lanes_per_warp, const void* d_samples_v, int sample_fmt,
                                       const unsigned long long* d_offsets, const uint32_t* d_lengths,
                                       cudaStream_t stream) {
   const uint32_t blocks = (p->n_streams + 31u) / 32u;
+  const int16_t* d_samples = static_cast<const int16_t*>(d_samples_v);
   // force_generic: 1 = generic kernel, 2 = single-warp fast kernel, 3 = pipelined four-warp kernel,
-  //                4 (or 0) = three-warp kernel.  The fast kernels need the 22050 Hz geometry (42 taps, DC length 16).
-  if (force_generic != 1 && p->ntaps == FAST_NTAPS && p->dc_len == FAST_DCL) {
+  //                4 (or 0) = three-warp kernel.  The fast kernels need the 22050 Hz geometry (42 taps, DC length 16)
+  //                and s16 samples (their DC blocker is an integer recursion).
+  if (sample_fmt == 0 && force_generic != 1 && p->ntaps == FAST_NTAPS && p->dc_len == FAST_DCL) {
     const uint32_t lanes = lanes_per_warp ? lanes_per_warp : 32u;
     const uint32_t fblocks = (p->n_streams + lanes - 1u) / lanes;
-    if (force_generic == 2)
+    if (force_generic == 2) {
       same_dev::same_rx_fast_kernel<<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes);
-    else if (force_generic == 3)
-{
+    } else if (force_generic == 3) {
       // per device, cheap: set on every launch rather than tracking which devices have seen it
       cudaError_t e = cudaFuncSetAttribute(same_dev::same_rx_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            PK_DYN_SMEM);
       if (e != cudaSuccess) return e;
       same_dev::same_rx_pipe_kernel<<<fblocks, PK_THREADS, PK_DYN_SMEM, stream>>>(*p, *taps2, d_samples, d_offsets,
                                                                                    d_lengths, lanes);
-    }
-    else
+    } else {
       same_dev::same_rx_ws_kernel<<<fblocks, WS_THREADS, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes);
-  } else if (p->ntaps <= 64 && p->dc_len <= 16) {
-    const size_t smem = (size_t)(64 + 2 * 16) * 32 * sizeof(float);
-    same_dev::same_rx_generic_kernel<64, 16><<<blocks, 32, smem, stream>>>(*p, *taps, d_samples, d_offsets, d_lengths);
+    }
   } else {
-    const size_t smem = (size_t)(128 + 2 * 64) * 32 * sizeof(float);
-    same_dev::same_rx_generic_kernel<128, 64><<<blocks, 32, smem, stream>>>(*p, *taps, d_samples, d_offsets, d_lengths);
+    const bool small = p->ntaps <= 64 && p->dc_len <= 16;
+    const size_t smem = small ? (size_t)(64 + 2 * 16) * 32 * sizeof(float) : (size_t)(128 + 2 * 64) * 32 * sizeof(float);
+    if (sample_fmt == 1) {
+      const float* f = static_cast<const float*>(d_samples_v);
+      if (small) same_dev::same_rx_generic_kernel<64, 16, float><<<blocks, 32, smem, stream>>>(*p, *taps, f, d_offsets, d_lengths);
+      else same_dev::same_rx_generic_kernel<128, 64, float><<<blocks, 32, smem, stream>>>(*p, *taps, f, d_offsets, d_lengths);
+    } else {
+      if (small) same_dev::same_rx_generic_kernel<64, 16, int16_t><<<blocks, 32, smem, stream>>>(*p, *taps, d_samples, d_offsets, d_lengths);
+      else same_dev::same_rx_generic_kernel<128, 64, int16_t><<<blocks, 32, smem, stream>>>(*p, *taps, d_samples, d_offsets, d_lengths);
+    }
   }
   return cudaGetLastError();
 }

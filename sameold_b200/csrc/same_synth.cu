@@ -25,20 +25,24 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 
 __global__ void synth_kernel(int16_t* __restrict__ out, uint32_t n_streams, unsigned long long stride,
-                             uint32_t n_samples, double rate, const uint32_t* __restrict__ burst_begin,
+                             uint32_t n_samples, unsigned long long first_group, double rate,
+                             const uint32_t* __restrict__ burst_begin,
                              const same_synth_burst* __restrict__ bursts, const uint8_t* __restrict__ bytes,
                              const uint16_t* __restrict__ cum_marks, const float* __restrict__ foff,
                              const uint32_t* __restrict__ seeds, float amplitude, float sigma) {
   const uint32_t stream = blockIdx.y;
-  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;  // group of 8 samples
-  const unsigned long long n0 = (unsigned long long)g * 8ull;
-  if (stream >= n_streams || n0 >= n_samples) return;
+  const uint32_t gl = blockIdx.x * blockDim.x + threadIdx.x;  // group of 8 samples inside this window
+  const unsigned long long l0 = (unsigned long long)gl * 8ull;  // first sample of the group, relative to the window
+  if (stream >= n_streams || l0 >= n_samples) return;
+  const unsigned long long g = first_group + gl;               // group index in the whole stream: noise counter
+  const unsigned long long n0 = g * 8ull;                      // absolute sample index
   const uint32_t seed = seeds[stream];
   float z[8];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     uint32_t r[4];
-    philox4x32_10((uint32_t)(2 * g + h), 0u, 0u, 0u, seed, 0u, r);
+    const unsigned long long ctr = 2ull * g + (unsigned long long)h;
+    philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, seed, 0u, r);
     float r0 = sqrtf(-2.0f * __logf(u01(r[0]))), r1 = sqrtf(-2.0f * __logf(u01(r[2])));
     float s0, c0, s1, c1;
     __sincosf(6.28318530718f * u01(r[1]), &s0, &c0);
@@ -75,8 +79,8 @@ __global__ void synth_kernel(int16_t* __restrict__ out, uint32_t n_streams, unsi
     q = max(-32768, min(32767, q));
     v[j] = (short)q;
   }
-  int16_t* dst = out + (unsigned long long)stream * stride + n0;
-  if (n0 + 8 <= n_samples && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+  int16_t* dst = out + (unsigned long long)stream * stride + l0;
+  if (l0 + 8 <= n_samples && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
     int4 pk;
     pk.x = (int)((uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16));
     pk.y = (int)((uint32_t)(uint16_t)v[2] | ((uint32_t)(uint16_t)v[3] << 16));
@@ -84,14 +88,14 @@ __global__ void synth_kernel(int16_t* __restrict__ out, uint32_t n_streams, unsi
     pk.w = (int)((uint32_t)(uint16_t)v[6] | ((uint32_t)(uint16_t)v[7] << 16));
     *reinterpret_cast<int4*>(dst) = pk;
   } else {
-    for (int j = 0; j < 8 && n0 + j < n_samples; ++j) dst[j] = v[j];
+    for (int j = 0; j < 8 && l0 + j < n_samples; ++j) dst[j] = v[j];
   }
 }
 
 }  // namespace
 
-extern "C" int same_synth_generate(int device, int16_t* d_out, uint32_t n_streams, uint64_t stride, uint32_t n_samples,
-                                   uint32_t rate, const uint32_t* burst_begin, const same_synth_burst* bursts,
+extern "C" int same_synth_generate(int device, int16_t* d_out, uint32_t n_streams, uint64_t stride, uint64_t first_sample,
+                                   uint32_t n_samples, uint32_t rate, const uint32_t* burst_begin, const same_synth_burst* bursts,
                                    uint32_t n_bursts, const uint8_t* bytes, uint64_t n_bytes_total,
                                    const float* freq_offset_hz, const uint32_t* seeds, float amplitude,
                                    float noise_sigma, char* err_text) {
@@ -100,6 +104,10 @@ extern "C" int same_synth_generate(int device, int16_t* d_out, uint32_t n_stream
   float* d_f = nullptr; uint32_t* d_s = nullptr;
   uint16_t* cum = nullptr;
 #define SCK(call) do { err = (call); if (err != cudaSuccess) goto done; } while (0)
+  if (first_sample % 8u) {
+    if (err_text) snprintf(err_text, 256, "first_sample must be a multiple of 8");
+    return (int)cudaErrorInvalidValue;
+  }
   SCK(cudaSetDevice(device));
   // marks before each byte, per burst
   cum = new uint16_t[n_bytes_total ? n_bytes_total : 1];
@@ -130,7 +138,7 @@ extern "C" int same_synth_generate(int device, int16_t* d_out, uint32_t n_stream
     for (uint32_t s0 = 0; s0 < n_streams; s0 += 32768u) {
       const uint32_t ns = (n_streams - s0 < 32768u) ? (n_streams - s0) : 32768u;
       dim3 grid((groups + 255u) / 256u, ns);
-      synth_kernel<<<grid, 256>>>(d_out + (unsigned long long)s0 * stride, ns, stride, n_samples, (double)rate,
+      synth_kernel<<<grid, 256>>>(d_out + (unsigned long long)s0 * stride, ns, stride, n_samples, first_sample / 8u, (double)rate,
                                   d_bb + s0, d_b, d_bytes, d_cum, d_f + s0, d_s + s0, amplitude, noise_sigma);
       SCK(cudaGetLastError());
     }

@@ -53,6 +53,10 @@ __device__ __noinline__ void emit_event_impl(const SameParams& p, uint32_t strea
     if ((unsigned long long)off + padded <= p.payload_cap) {
       if ((reinterpret_cast<uintptr_t>(data) & 3u) == 0) copy_words(p.payload + off, data, copy_len);
       else for (uint32_t i = 0; i < copy_len; ++i) p.payload[off + i] = data[i];
+    } else {
+      // payload arena full: the event is still delivered, without bytes, and says so (never an offset past the arena)
+      atomicAdd(&p.counters[2], 1u);
+      off = 0; data_len = 0; flags |= SAME_EV_FLAG_PAYLOAD_LOST;
     }
   }
   if (idx < p.events_cap) {

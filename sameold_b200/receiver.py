@@ -251,6 +251,10 @@ class SameReceiverBuilder:
         """The batched entry point: n_streams independent receivers resident on one GPU."""
         return SameBatchReceiver(self.config(), n_streams, device)
 
+    def build_multi(self, n_streams: int, devices: Sequence[int]) -> "SameMultiReceiver":
+        """n_streams receivers sharded over several GPUs of this box (one host thread + engine per device)."""
+        return SameMultiReceiver(self.config(), n_streams, devices)
+
 
 # ---------------------------------------------------------------------------------------------------------------------
 # Batched receiver
@@ -342,6 +346,34 @@ class SameBatchReceiver:
         self._keep = (flat, offsets, lengths)
         self._ck(self._lib.same_engine_submit_s16(self._h, flat.ctypes.data, flat.size, offsets.ctypes.data, lengths.ctypes.data))
 
+    def submit_f32(self, chunks):
+        """Feed one chunk of f32 samples per stream — the reference's own item type (receiver.rs:119-130; lib.rs:78-79:
+        any scale, the AGC normalises).  Takes the literal f32 DC-blocker recursion (rate-generic kernel)."""
+        if isinstance(chunks, np.ndarray) and chunks.ndim == 2:
+            arrs = [np.ascontiguousarray(r, dtype=np.float32) for r in chunks]
+        else:
+            arrs = [np.zeros(0, np.float32) if c is None else np.ascontiguousarray(c, dtype=np.float32).reshape(-1) for c in chunks]
+        if len(arrs) != self.n_streams:
+            raise ValueError(f"expected {self.n_streams} chunks, got {len(arrs)}")
+        lengths = np.array([a.size for a in arrs], np.uint32)
+        offsets = np.zeros(len(arrs), np.uint64)
+        if len(arrs) > 1:
+            offsets[1:] = np.cumsum(lengths[:-1], dtype=np.uint64)
+        flat = np.concatenate(arrs) if arrs else np.zeros(0, np.float32)
+        self._keep = (flat, offsets, lengths)
+        self._ck(self._lib.same_engine_submit_f32(self._h, flat.ctypes.data, flat.size, offsets.ctypes.data, lengths.ctypes.data))
+
+    def process_f32(self, chunks) -> List[List[SameReceiverEvent]]:
+        self.submit_f32(chunks)
+        self.sync()
+        return self.drain_by_stream()
+
+    def lost_events(self):
+        """(events dropped, payloads dropped) because an arena was full, since create."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self._lib.same_engine_lost_events(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def submit_flat(self, flat: np.ndarray, offsets: np.ndarray, lengths: np.ndarray):
         """Zero-copy variant: caller-owned flat int16 buffer (e.g. pinned) + per-stream offsets/lengths."""
         assert flat.dtype == np.int16 and offsets.dtype == np.uint64 and lengths.dtype == np.uint32
@@ -386,6 +418,19 @@ class SameBatchReceiver:
             out.append(SameReceiverEvent(e.stream, e.kind, e.input_sample_counter, e.symbol_count,
                                          payload[e.data_offset: e.data_offset + n], e.err, e.parity_errors,
                                          e.voting_bytes, e.flags))
+        return out
+
+    @staticmethod
+    def events_from_raw(evs: np.ndarray, pay: np.ndarray) -> List[SameReceiverEvent]:
+        """same_event records (drain_raw) -> SameReceiverEvent objects."""
+        payload = pay.tobytes()
+        out = []
+        for e in evs:
+            n = min(int(e["data_len"]), 1024) if e["kind"] == EV_LINK_BURST else int(e["data_len"])
+            o = int(e["data_offset"])
+            out.append(SameReceiverEvent(int(e["stream"]), int(e["kind"]), int(e["sample"]), int(e["symbol_count"]),
+                                         payload[o:o + n], int(e["err"]), int(e["parity_errors"]),
+                                         int(e["voting_bytes"]), int(e["flags"])))
         return out
 
     EVENT_DTYPE = np.dtype([("stream", "<u4"), ("seq", "<u4"), ("sample", "<u8"), ("symbol_count", "<u8"),
@@ -486,6 +531,11 @@ class SameBatchReceiver:
     def set_option(self, key: str, value: int):
         self._ck(self._lib.same_engine_set_option(self._h, key.encode(), int(value)))
 
+    def get_option(self, key: str) -> int:
+        v = C.c_int()
+        self._ck(self._lib.same_engine_get_option(self._h, key.encode(), C.byref(v)))
+        return v.value
+
     def last_timing(self):
         h2d, k = C.c_float(), C.c_float()
         self._ck(self._lib.same_engine_last_timing(self._h, C.byref(h2d), C.byref(k)))
@@ -515,6 +565,112 @@ class SameBatchReceiver:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# One batch over several GPUs of a box, inside one process (same_multi_* in include/same_engine.h)
+# ---------------------------------------------------------------------------------------------------------------------
+class SameMultiReceiver:
+    """n_streams receivers sharded contiguously over `devices`: one engine + one host thread per device inside the
+    native library, no collective (streams are independent).  Events carry global stream ids."""
+
+    def __init__(self, cfg, n_streams: int, devices: Sequence[int]):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        rc = self._lib.same_multi_create(C.byref(cfg), devs, len(devices), int(n_streams), C.byref(self._h))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise SameEngineError(rc, self._lib.same_multi_last_error(None).decode())
+        self.n_streams = int(n_streams)
+        self.devices = [int(d) for d in devices]
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.same_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SameEngineError(rc, self._lib.same_multi_last_error(self._h).decode())
+
+    def shards(self):
+        """[(device, first_stream, n_streams)] per shard."""
+        out = []
+        for i in range(self._lib.same_multi_num_shards(self._h)):
+            d, f, n = C.c_int(), C.c_uint32(), C.c_uint32()
+            self._lib.same_multi_shard_info(self._h, i, C.byref(d), C.byref(f), C.byref(n))
+            out.append((d.value, f.value, n.value))
+        return out
+
+    def set_option(self, key: str, value: int):
+        for i in range(len(self.devices)):
+            eng = C.c_void_p(self._lib.same_multi_engine(self._h, i))
+            rc = self._lib.same_engine_set_option(eng, key.encode(), int(value))
+            if rc != 0:
+                raise SameEngineError(rc, self._lib.same_engine_last_error(eng).decode())
+
+    def submit(self, chunks):
+        flat, offsets, lengths = SameBatchReceiver._pack(chunks)
+        if lengths.size != self.n_streams:
+            raise ValueError(f"expected {self.n_streams} chunks, got {lengths.size}")
+        self._keep = (flat, offsets, lengths)
+        self._ck(self._lib.same_multi_submit_s16(self._h, flat.ctypes.data, flat.size, offsets.ctypes.data, lengths.ctypes.data))
+
+    def submit_2d(self, host_ptr: int, row_stride: int, col_start: int, n_cols: int):
+        self._ck(self._lib.same_multi_submit_s16_2d(self._h, C.c_void_p(host_ptr), int(row_stride), int(col_start), int(n_cols)))
+
+    def submit_zeros(self, lengths):
+        lengths = np.ascontiguousarray(np.broadcast_to(np.asarray(lengths, dtype=np.uint32), (self.n_streams,)))
+        self._keep = (lengths,)
+        self._ck(self._lib.same_multi_submit_zeros(self._h, lengths.ctypes.data))
+
+    def sync(self):
+        self._ck(self._lib.same_multi_sync(self._h))
+        self._keep = None
+
+    def reset(self):
+        self._ck(self._lib.same_multi_reset(self._h))
+
+    def input_sample_counters(self) -> np.ndarray:
+        out = np.zeros(self.n_streams, np.uint64)
+        self._ck(self._lib.same_multi_input_sample_counters(self._h, out.ctypes.data))
+        return out
+
+    def drain_raw(self):
+        nev, npay = C.c_size_t(), C.c_size_t()
+        self._ck(self._lib.same_multi_pending(self._h, C.byref(nev), C.byref(npay)))
+        evs = np.empty(nev.value, SameBatchReceiver.EVENT_DTYPE)
+        pay = np.empty(max(npay.value, 1), np.uint8)
+        if nev.value:
+            self._ck(self._lib.same_multi_drain_events(self._h, evs.ctypes.data, evs.size, C.byref(nev), pay.ctypes.data,
+                                                       pay.size, C.byref(npay)))
+        return evs[: nev.value], pay[: npay.value]
+
+    def drain_by_stream(self) -> List[List[SameReceiverEvent]]:
+        out: List[List[SameReceiverEvent]] = [[] for _ in range(self.n_streams)]
+        for e in SameBatchReceiver.events_from_raw(*self.drain_raw()):
+            out[e.stream].append(e)
+        return out
+
+    def process(self, chunks) -> List[List[SameReceiverEvent]]:
+        self.submit(chunks)
+        self.sync()
+        return self.drain_by_stream()
+
+    def iter_messages_batched(self, chunks) -> Iterator["tuple[int, Message]"]:
+        """== iter_messages (receiver.rs:155-161) for every stream of the whole box: yields (stream, Message)."""
+        for evs in self.process(chunks):
+            for e in evs:
+                m = e.message_ok()
+                if m is not None:
+                    yield (e.stream, m)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # Single-stream facade with the reference's method names
 # ---------------------------------------------------------------------------------------------------------------------
 class SameReceiver:
@@ -539,29 +695,31 @@ class SameReceiver:
         self._b.reset()
 
     def _blocks(self, source) -> Iterator[np.ndarray]:
+        """int16 arrays (and iterables of Python ints) go in as s16 PCM — what samedec feeds (`sa as f32`, app.rs:112);
+        anything else is the reference's own f32 item type and goes in as f32, whatever its scale."""
         if isinstance(source, np.ndarray):
-            a = source
+            a = source.reshape(-1)
             if a.dtype != np.int16:
-                # the reference takes f32 samples that samedec produced with `sa as f32` from i16 (app.rs:112);
-                # the engine ingests the i16 directly
-                if not np.all(a == np.round(a)) or np.any(np.abs(a) > 32768):
-                    raise ValueError("SameReceiver ingests s16 PCM (integer-valued samples in the i16 range)")
-                a = a.astype(np.int16)
+                a = a.astype(np.float32, copy=False)
             for i in range(0, a.size, self.BLOCK):
                 yield a[i:i + self.BLOCK]
             return
-        buf = []
+        buf, is_int = [], True
         for v in source:
+            is_int = is_int and isinstance(v, (int, np.integer)) and -32768 <= v <= 32767
             buf.append(v)
             if len(buf) >= self.BLOCK:
-                yield np.asarray(buf, dtype=np.int16)
-                buf = []
+                yield np.asarray(buf, dtype=np.int16 if is_int else np.float32)
+                buf, is_int = [], True
         if buf:
-            yield np.asarray(buf, dtype=np.int16)
+            yield np.asarray(buf, dtype=np.int16 if is_int else np.float32)
 
     def iter_events(self, source: Iterable) -> Iterator[SameReceiverEvent]:   # receiver.rs:119-130
         for blk in self._blocks(source):
-            yield from self._b.process([blk])[0]
+            if blk.dtype == np.int16:
+                yield from self._b.process([blk])[0]
+            else:
+                yield from self._b.process_f32([blk])[0]
 
     def iter_messages(self, source: Iterable) -> Iterator[Message]:           # receiver.rs:155-161
         for e in self.iter_events(source):

@@ -70,36 +70,80 @@ def plan_stream(stream_id: int, rate: int = 22050, seconds: float = 60.0, seed_b
     return StreamPlan(hdr, [k[0] for k in keep], [k[1] for k in keep], foff, (seed_base + int(stream_id)) & 0xFFFFFFFF)
 
 
+def plan_long_stream(hours: float = 24.0, rate: int = 22050, seed: int = 0x24C0FFEE) -> StreamPlan:
+    """ONE continuous stream, a SAME event (3 header + 3 EOM bursts, 1 s gaps, EOMs U(5,20) s after
+    the header) every U(10,60) minutes, AWGN over the whole length."""
+    r = np.random.Generator(np.random.Philox(key=seed))
+    total = hours * 3600.0 * rate
+    sym = rate / 520.83
+    starts, payloads = [], []
+    t = float(r.uniform(10.0, 60.0)) * 60.0 * rate
+    k = 0
+    first_header = ""
+    while True:
+        ev = plan_stream(100000 + k, rate, 120.0)      # header text / payloads of one event (its own start is ignored)
+        first_header = first_header or ev.header
+        hb, eb = PREAMBLE + ev.header.encode("ascii"), PREAMBLE + b"NNNN"
+        gap = float(r.uniform(5.0, 20.0))
+        t0, ss, pp = t, [], []
+        for _ in range(3):
+            ss.append(t0); pp.append(hb); t0 += len(hb) * 8 * sym + 1.0 * rate
+        t0 += (gap - 1.0) * rate
+        for _ in range(3):
+            ss.append(t0); pp.append(eb); t0 += len(eb) * 8 * sym + 1.0 * rate
+        if t0 + rate >= total:
+            break
+        starts += ss; payloads += pp
+        t = t0 + float(r.uniform(10.0, 60.0)) * 60.0 * rate
+        k += 1
+    return StreamPlan(first_header, starts, payloads, float(r.uniform(-5.0, 5.0)), seed & 0xFFFFFFFF)
+
+
 def plan_corpus(n_streams: int, rate: int = 22050, seconds: float = 60.0, first_stream: int = 0,
                 seed_base: int = SEED_BASE) -> List[StreamPlan]:
     return [plan_stream(first_stream + i, rate, seconds, seed_base) for i in range(n_streams)]
 
 
+class DeviceCorpus:
+    """The burst tables of a list of plans, packed once; `generate` renders any time window of every stream."""
+
+    def __init__(self, plans: List[StreamPlan], rate: int = 22050, device: int = 0, amplitude: float = AMPLITUDE,
+                 noise_sigma: float = NOISE_SIGMA):
+        self.lib = _lib.load()
+        self.n, self.rate, self.device, self.amplitude, self.noise_sigma = len(plans), rate, device, amplitude, noise_sigma
+        self.begin = np.zeros(self.n + 1, np.uint32)
+        bursts, blobs, off = [], [], 0
+        for i, p in enumerate(plans):
+            for s, b in zip(p.burst_starts, p.burst_payloads):
+                bursts.append((s, off, len(b)))
+                blobs.append(b)
+                off += len(b)
+            self.begin[i + 1] = len(bursts)
+        self.nbursts, self.nbytes = len(bursts), off
+        self.barr = (_SynthBurst * max(len(bursts), 1))()
+        for k, (s, o, l) in enumerate(bursts):
+            self.barr[k].start_sample, self.barr[k].byte_offset, self.barr[k].n_bytes = s, o, l
+        self.data = np.frombuffer(b"".join(blobs) or b"\0", dtype=np.uint8).copy()
+        self.foff = np.array([p.freq_offset_hz for p in plans], np.float32)
+        self.seeds = np.array([p.seed for p in plans], np.uint32)
+
+    def generate(self, d_ptr: int, stride: int, n_samples: int, first_sample: int = 0):
+        """d_ptr[stream * stride + k] = sample first_sample + k of each stream, k < n_samples (first_sample % 8 == 0)."""
+        err = C.create_string_buffer(256)
+        rc = self.lib.same_synth_generate(self.device, C.c_void_p(d_ptr), self.n, stride, int(first_sample), n_samples,
+                                          self.rate, self.begin.ctypes.data, self.barr, self.nbursts,
+                                          self.data.ctypes.data, self.nbytes, self.foff.ctypes.data,
+                                          self.seeds.ctypes.data, self.amplitude, self.noise_sigma, err)
+        if rc != 0:
+            raise RuntimeError(f"same_synth_generate failed: {err.value.decode()}")
+
+
 def generate_on_device(plans: List[StreamPlan], d_ptr: int, stride: int, n_samples: int, rate: int = 22050,
-                       device: int = 0, amplitude: float = AMPLITUDE, noise_sigma: float = NOISE_SIGMA):
-    """Fill device memory d_ptr[stream * stride + n] (int16) with the corpus described by `plans`."""
-    lib = _lib.load()
-    n = len(plans)
-    begin = np.zeros(n + 1, np.uint32)
-    bursts, blobs, off = [], [], 0
-    for i, p in enumerate(plans):
-        for s, b in zip(p.burst_starts, p.burst_payloads):
-            bursts.append((s, off, len(b)))
-            blobs.append(b)
-            off += len(b)
-        begin[i + 1] = len(bursts)
-    barr = (_SynthBurst * max(len(bursts), 1))()
-    for k, (s, o, l) in enumerate(bursts):
-        barr[k].start_sample, barr[k].byte_offset, barr[k].n_bytes = s, o, l
-    data = np.frombuffer(b"".join(blobs) or b"\0", dtype=np.uint8).copy()
-    foff = np.array([p.freq_offset_hz for p in plans], np.float32)
-    seeds = np.array([p.seed for p in plans], np.uint32)
-    err = C.create_string_buffer(256)
-    rc = lib.same_synth_generate(device, C.c_void_p(d_ptr), n, stride, n_samples, rate, begin.ctypes.data, barr,
-                                 len(bursts), data.ctypes.data, off, foff.ctypes.data, seeds.ctypes.data,
-                                 amplitude, noise_sigma, err)
-    if rc != 0:
-        raise RuntimeError(f"same_synth_generate failed: {err.value.decode()}")
+                       device: int = 0, amplitude: float = AMPLITUDE, noise_sigma: float = NOISE_SIGMA,
+                       first_sample: int = 0):
+    """Fill device memory d_ptr[stream * stride + k] (int16) with samples [first_sample, first_sample + n_samples) of
+    the corpus described by `plans`."""
+    DeviceCorpus(plans, rate, device, amplitude, noise_sigma).generate(d_ptr, stride, n_samples, first_sample)
 
 
 def render_numpy(plan: StreamPlan, n_samples: int, rate: int = 22050, amplitude: float = AMPLITUDE,

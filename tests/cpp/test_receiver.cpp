@@ -55,6 +55,17 @@ int main(int argc, char** argv) {
     CHECK(m && m->is_start && m->text == lines[0][0] && m->voting_byte_count == 252 && m->parity_error_count == 0);
     CHECK(one.input_sample_counter() > recs[0].size() && one.input_sample_counter() < recs[0].size() + 4 * 22050);
     CHECK(!one.flush());
+    // the reference's own item type: f32 PCM normalised to [-1, 1) (lib.rs:78-79), library-default builder (AGC limits
+    // [0, 1e6], builder.rs:55) -- the same header comes out
+    {
+      auto fb = same::SameReceiverBuilder(22050);
+      std::vector<float> f(recs[1].size());
+      for (size_t i = 0; i < f.size(); ++i) f[i] = (float)recs[1][i] / 32768.0f;
+      auto fr = fb.build();
+      auto fm = fr.iter_messages(f);
+      CHECK(fm.size() == 1 && fm[0].is_start && fm[0].text == lines[1][0]);
+      CHECK(fr.input_sample_counter() == f.size());
+    }
     std::printf("CPP_OK\n");
     return 0;
   } catch (const same::EngineError& e) {

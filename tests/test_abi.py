@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_struct_sizes():
     lib = _lib.load()
-    assert lib.same_abi_version() == 1
+    assert lib.same_abi_version() == 2
     assert C.sizeof(_lib.SameConfig) == 19 * 4
     assert C.sizeof(_lib.SameEvent) == 48
     assert C.sizeof(_lib.SameSoftSymbol) == 16
@@ -138,3 +138,18 @@ def test_rust_ffi_declares_the_whole_header():
 
     for name in ("same_config", "same_event", "same_soft_symbol", "same_derived"):
         assert c_fields(name) == rust_fields(name), name
+
+
+def test_library_reads_no_environment_variables():
+    """a host application's environment must not be able to override the measured kernel policy; the only
+    override is same_engine_set_option."""
+    for f in os.listdir(os.path.join(ROOT, "sameold_b200", "csrc")):
+        txt = open(os.path.join(ROOT, "sameold_b200", "csrc", f), errors="ignore").read()
+        assert "getenv" not in txt, f
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-GPU failure mode")
+def test_multi_device_entry_is_loud_without_gpu():
+    with pytest.raises(sb.SameEngineError) as ei:
+        sb.SameReceiverBuilder(22050).build_multi(64, [0, 0])
+    assert ei.value.code == 3

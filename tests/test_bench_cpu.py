@@ -30,6 +30,8 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"] and "model" not in line["config"]
+    # the reference arm runs the CPU port only: none of the product's native code is loaded
+    assert line["native_so_loaded"] == ["oracle/_build/liboracle.so"], line["native_so_loaded"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():

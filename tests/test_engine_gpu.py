@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import sameold_b200 as sb
-from oracle import GOLDEN_DIR, Oracle, load_golden_recording
+from oracle import GOLDEN_DIR, Oracle, decode_batch_events, load_golden_recording
 from oracle.pyoracle import OracleConfig
 from sameold_b200 import synth
 
@@ -229,7 +229,7 @@ def test_fast_and_generic_kernels_agree():
     recs = [load_golden_recording(n) for n in NAMES] + [synth.render_numpy(synth.plan_stream(5, seconds=20.0), 20 * 22050)]
     b = sb.SameReceiverBuilder.samedec(22050)
     ref = b.build_batch(len(recs))
-    ref.set_option("force_generic", 1)
+    ref.set_option("kernel", 1)
     want = ref.process(recs)
     rx = b.build_batch(len(recs))
     rng = np.random.default_rng(11)
@@ -237,7 +237,7 @@ def test_fast_and_generic_kernels_agree():
     got = [[] for _ in recs]
     k = 0
     while any(p < len(r) for p, r in zip(pos, recs)):
-        rx.set_option("force_generic", 1 + k % 4)   # 1 generic, 2 single-warp fast, 3 pipelined, 4 three-warp
+        rx.set_option("kernel", 1 + k % 4)   # 1 generic, 2 single-warp fast, 3 pipelined, 4 three-warp
         k += 1
         chunks = []
         for s_ in range(len(recs)):
@@ -267,12 +267,12 @@ def test_each_fast_kernel_matches_oracle(kernel):
         o.process_s16(r)
         want.append(o.events())
     rx = b.build_batch(len(recs))
-    rx.set_option("force_generic", kernel)
+    rx.set_option("kernel", kernel)
     got = rx.process(recs)
     for s_ in range(len(recs)):
         assert_events_equal(got[s_], want[s_], f"kernel {kernel} stream {s_} one submit")
     rx = b.build_batch(len(recs))
-    rx.set_option("force_generic", kernel)
+    rx.set_option("kernel", kernel)
     got = [[] for _ in recs]
     step = 3 * 22050 + 7
     for lo in range(0, max(len(r) for r in recs), step):
@@ -287,6 +287,7 @@ def _canonical_raw(evs, pay):
     bytes concatenated in event order."""
     e = evs.copy()
     off, ln = e["data_offset"].astype(np.int64), e["data_len"].astype(np.int64)
+    ln = np.where(e["kind"] == 3, np.minimum(ln, 1024), ln)     # burst payloads are capped at SAME_BURST_CAP
     e["data_offset"] = 0
     idx = np.repeat(off - np.concatenate(([0], np.cumsum(ln)[:-1])), ln) + np.arange(int(ln.sum()))
     return e, pay[idx]
@@ -305,7 +306,7 @@ def test_large_batches_engine_policy_matches_generic_kernel(ns):
     got = []
     for kernel in (0, 1):
         rx = b.build_batch(ns)
-        rx.set_option("force_generic", kernel)
+        rx.set_option("kernel", kernel)
         rx.submit_device(buf.data_ptr(), ns * stride, offsets, lengths)
         rx.sync()
         got.append(_canonical_raw(*rx.drain_raw()))
@@ -324,26 +325,57 @@ def test_large_batches_engine_policy_matches_generic_kernel(ns):
         assert_events_equal(by_stream[s_], o.events(), f"stream {s_} of {ns}")
 
 
-def test_config3_full_size_kernels_agree_and_are_deterministic():
-    """BASELINE config 3 at full size (4096 streams x 60 s, 10.8 GB of samples): the engine's kernel for this batch
-    size (pipelined), run three times, and every other kernel once must produce the same event stream; every stream
-    must decode its header, and the burst payloads must carry the planned header text."""
+def _assert_raw_equal(got, want, ctx):
+    """Whole event arrays (engine same_event records vs the oracle's, both canonicalised) must be identical; on a
+    mismatch report the first differing stream/event."""
+    (ge, gp), (we, wp) = got, want
+    if ge.size == we.size and np.array_equal(ge, we) and np.array_equal(gp, wp):
+        return
+    n = min(ge.size, we.size)
+    bad = np.nonzero(ge[:n] != we[:n])[0]
+    i = int(bad[0]) if bad.size else n
+    raise AssertionError(f"{ctx}: {ge.size} engine events vs {we.size} oracle events; first difference at event {i}:\n"
+                         f"  engine {ge[i] if i < ge.size else None}\n  oracle {we[i] if i < we.size else None}")
+
+
+def _rebase_seq(evs):
+    """Per-stream sequence numbers counted from 0 (the engine's count from create/reset; the oracle batch export's
+    always from 0) -- `evs` is sorted by (stream, seq)."""
+    e = evs.copy()
+    if e.size:
+        first = np.concatenate(([True], e["stream"][1:] != e["stream"][:-1]))
+        base = np.maximum.accumulate(np.where(first, np.arange(e.size), 0))
+        e["seq"] = (np.arange(e.size) - base).astype(np.uint32)
+    return e
+
+
+def test_config3_full_size_every_stream_vs_oracle():
+    """BASELINE config 3 at full size (4096 streams x 60 s, 10.8 GB of samples), BASELINE.md §3 row 3: the engine's
+    events on EVERY stream are bit-identical to the CPU oracle's (kind, sample counter, symbol count, bytes, parity /
+    voting counts); the engine's kernel for this batch size (pipelined) run three times, and every other kernel once,
+    produce the same event stream; every stream decodes its planned header."""
     _torch()
     ns, secs = 4096, 60.0
     buf, plans, n, stride = _device_corpus(ns, secs)
     offsets = np.arange(ns, dtype=np.uint64) * np.uint64(stride)
     lengths = np.full(ns, n, np.uint32)
     b = sb.SameReceiverBuilder.samedec(22050)
+    # the oracle on all 4096 x 60 s, one receiver per stream, every host core
+    host = buf.cpu().numpy()
+    oe, op, osecs = decode_batch_events(oracle_cfg_from(b), host[:, :n], os.cpu_count() or 1)
+    want = _canonical_raw(oe, op)
+    del host
     ref = None
     for kernel in (0, 0, 0, 1, 2, 4):
         rx = b.build_batch(ns)
-        rx.set_option("force_generic", kernel)
+        rx.set_option("kernel", kernel)
         rx.submit_device(buf.data_ptr(), ns * stride, offsets, lengths)
         rx.sync()
         evs, pay = _canonical_raw(*rx.drain_raw())
         del rx
         if ref is None:
             ref = (evs, pay)
+            _assert_raw_equal((evs, pay), want, "config 3, all 4096 streams, engine vs oracle")
             som = evs[evs["kind"] == 18]
             assert np.array_equal(np.unique(som["stream"]), np.arange(ns)), "every stream decodes its header"
         else:
@@ -357,6 +389,52 @@ def test_config3_full_size_kernels_agree_and_are_deterministic():
     for s_ in (0, 1, 777, 4095):
         msgs = [e for e in by_stream[s_] if e.kind == 18]
         assert msgs and bytes(msgs[0].data).decode("ascii") == plans[s_].header, f"stream {s_}"
+
+
+def test_config4_65536_streams_time_chunked_two_shards_vs_oracle():
+    """BASELINE config 4: 65 536 synthetic 60 s streams (173 GB of samples: more than one GPU holds), streamed through
+    in 10 s time-chunks with the receiver state resident, as two contiguous 32 768-stream shards (one engine + one
+    host thread each, same_multi_*).  Every 64th stream (1024 streams, all 60 s) is compared with the oracle event
+    for event; chunked == whole follows from receiver.rs:233-274."""
+    torch = _torch()
+    ns, secs, chunk_s, every = 65536, 60.0, 10.0, 64
+    rate = 22050
+    n, cn = int(secs * rate), int(chunk_s * rate)
+    assert cn % 8 == 0 and n % cn == 0
+    plans = synth.plan_corpus(ns, rate, secs)
+    corpus = synth.DeviceCorpus(plans, rate)
+    buf = torch.empty((ns, cn), dtype=torch.int16, device="cuda")
+    b = sb.SameReceiverBuilder.samedec(rate)
+    rx = b.build_multi(ns, [0, 0])
+    assert [(f, c) for _, f, c in rx.shards()] == [(0, 32768), (32768, 32768)]
+    host = torch.empty((ns // every, n), dtype=torch.int16, pin_memory=False)
+    offsets = np.arange(ns, dtype=np.uint64) * np.uint64(cn)
+    lengths = np.full(ns, cn, np.uint32)
+    import ctypes as C
+    lib = rx._lib
+    evs_all, pay_all, pay_base = [], [], 0
+    for c in range(n // cn):
+        corpus.generate(buf.data_ptr(), cn, cn, first_sample=c * cn)
+        host[:, c * cn:(c + 1) * cn] = buf[::every].cpu()
+        for i, (_dev, first, count) in enumerate(rx.shards()):   # device-resident chunk: each shard's engine takes its rows
+            eng = C.c_void_p(lib.same_multi_engine(rx._h, i))
+            rc = lib.same_engine_submit_s16_device(eng, C.c_void_p(buf.data_ptr() + first * cn * 2), count * cn,
+                                                   offsets[:count].ctypes.data, lengths[:count].ctypes.data)
+            assert rc == 0
+        rx.sync()
+        e, p = rx.drain_raw()
+        e = e.copy(); e["data_offset"] += pay_base
+        evs_all.append(e); pay_all.append(p.copy()); pay_base += p.size
+    assert np.array_equal(rx.input_sample_counters(), np.full(ns, n, np.uint64))
+    evs = np.concatenate(evs_all); pay = np.concatenate(pay_all)
+    order = np.lexsort((evs["seq"], evs["stream"]))          # per-chunk batches -> global (stream, occurrence) order
+    evs = evs[order]
+    assert int((evs["kind"] == 18).sum()) >= int(0.95 * ns), "the corpus is decodable"
+    sel = evs[evs["stream"] % every == 0]
+    sel["stream"] //= every
+    got = _canonical_raw(_rebase_seq(sel), pay)
+    oe, op, _ = decode_batch_events(oracle_cfg_from(b), host.numpy(), os.cpu_count() or 1)
+    _assert_raw_equal(got, _canonical_raw(oe, op), "config 4, 1024 sampled streams, engine vs oracle")
 
 
 def test_device_and_host_event_sort_agree():
@@ -536,10 +614,221 @@ def test_snapshot_restore_is_clone():
     assert len(a) + len(b1) > 10
 
 
-def test_event_overflow_is_reported():
+def test_event_overflow_is_reported_and_stays_consistent():
+    """Arena too small: sync reports SAME_ERR_EVENT_OVERFLOW once; what is then drained is self-consistent
+    (no payload offset past the arena; lost payloads flagged, lost events counted); the engine keeps working."""
     _torch()
-    rx = sb.SameReceiverBuilder.samedec(22050).build_batch(1)
-    rx.set_event_capacity(2, 16)
+    rec = load_golden_recording("npt")
+    b = sb.SameReceiverBuilder.samedec(22050)
+    want = b.build_batch(1).process([rec])[0]
+    rx = b.build_batch(1)
+    rx.set_event_capacity(4, 48)          # room for 4 events and one 45-byte burst
     with pytest.raises(sb.SameEngineError) as ei:
-        rx.process([load_golden_recording("npt")])
+        rx.process([rec])
     assert ei.value.code == 5
+    evs, pay = rx.drain_raw()
+    assert evs.size == 4 and pay.size <= 48
+    stored = np.where(evs["kind"] == 3, np.minimum(evs["data_len"], 1024), evs["data_len"])
+    assert np.all(evs["data_offset"].astype(np.int64) + stored <= pay.size)
+    for g, w in zip(sb.SameBatchReceiver.events_from_raw(evs, pay), want):
+        assert (g.kind, g.sample, g.symbol_count) == (w.kind, w.sample, w.symbol_count)
+        assert g.data == w.data or (g.flags & 2 and g.data == b"")
+    lost_ev, lost_pay = rx.lost_events()
+    assert lost_ev == len(want) - 4
+    # with a big enough arena the same engine carries on: chunked == whole still holds for what follows
+    rx.set_event_capacity(65536, 1 << 20)
+    o = Oracle(oracle_cfg_from(b))
+    o.process_s16(rec)
+    o.process_s16(rec)
+    n_first = len(want)
+    assert_events_equal(rx.process([rec])[0], o.events()[n_first:], "after the overflow")
+    # payload arena smaller than one burst: the event arrives without bytes and says so
+    rx2 = b.build_batch(1)
+    rx2.set_event_capacity(1024, 16)
+    with pytest.raises(sb.SameEngineError):
+        rx2.process([rec])
+    evs, pay = rx2.drain_raw()
+    bursts = evs[evs["kind"] == 3]
+    assert bursts.size == 3 and np.all(bursts["data_len"] == 0) and np.all(bursts["flags"] & 2)
+    assert rx2.lost_events()[1] >= 3
+
+
+def test_f32_ingest_matches_oracle():
+    """The reference's own item type (iter_events<Item = f32>, receiver.rs:119-130; lib.rs:78-79 documents f32 PCM):
+    normalised, non-integer samples with the library-default AGC limits [0, 1e6] (builder.rs:55) and with samedec's
+    limits on unnormalised floats, whole and chunked, bit-exact against the oracle's f32 entry."""
+    _torch()
+    rng = np.random.default_rng(21)
+    recs = [load_golden_recording(n) for n in NAMES]
+    cases = [(sb.SameReceiverBuilder(22050), np.float32(1.0 / 32768.0)),
+             (sb.SameReceiverBuilder.samedec(22050), np.float32(0.7301)),
+             (sb.SameReceiverBuilder.samedec(44100), np.float32(0.25))]
+    for b, scale in cases:
+        if b.input_rate() == 22050:
+            xs = [r.astype(np.float32) * scale for r in recs]
+        else:
+            plan = synth.plan_stream(78, b.input_rate(), 20.0)
+            xs = [synth.render_numpy(plan, int(20 * b.input_rate()), b.input_rate()).astype(np.float32) * scale]
+        want = []
+        for x in xs:
+            o = Oracle(oracle_cfg_from(b))
+            o.process_f32(x)
+            want.append(o.events())
+        assert any(e.kind in (18, 19) for w in want for e in w)
+        got = b.build_batch(len(xs)).process_f32(xs)
+        for s_ in range(len(xs)):
+            assert_events_equal(got[s_], want[s_], f"f32 x{scale} stream {s_} one submit")
+        rx = b.build_batch(len(xs))
+        got = [[] for _ in xs]
+        pos = [0] * len(xs)
+        while any(p < len(x) for p, x in zip(pos, xs)):
+            chunks = []
+            for s_ in range(len(xs)):
+                k = int(rng.integers(1, 50000))
+                chunks.append(xs[s_][pos[s_]:pos[s_] + k]); pos[s_] += len(chunks[-1])
+            for s_, e in enumerate(rx.process_f32(chunks)):
+                got[s_].extend(e)
+        for s_ in range(len(xs)):
+            assert_events_equal(got[s_], want[s_], f"f32 x{scale} stream {s_} chunked")
+
+
+def test_f32_then_s16_on_one_engine_and_facade():
+    """After an f32 chunk the DC-blocker windows may hold non-integers: the engine must stay on the literal f32
+    recursion for later s16 chunks (until reset).  Also the single-stream facade with float arrays."""
+    _torch()
+    rec = load_golden_recording("two_and_two")
+    b = sb.SameReceiverBuilder.samedec(22050)
+    half = 70001
+    xf = rec[:half].astype(np.float32) + np.float32(0.37)      # non-integer DC offset
+    o = Oracle(oracle_cfg_from(b))
+    o.process_f32(xf)
+    o.process_s16(rec[half:])
+    rx = b.build_batch(1)
+    assert rx.get_option("kernel_selected") == 3
+    got = rx.process_f32([xf])[0]
+    assert rx.get_option("kernel_selected") == 1
+    got += rx.process([rec[half:]])[0]
+    assert_events_equal(got, o.events(), "f32 chunk then s16 chunk")
+    rx.reset()
+    assert rx.get_option("kernel_selected") == 3
+    # facade: float arrays take the f32 entry, int16 arrays the s16 one
+    one = sb.SameReceiverBuilder(22050).build()
+    x = load_golden_recording("npt").astype(np.float32) / np.float32(32768.0)
+    msgs = [str(m) for m in one.iter_messages(x)]
+    assert msgs == expected_lines("npt")
+
+
+def test_submit_2d_odd_columns_from_pinned_host_memory():
+    """same_engine_submit_s16_2d with odd chunk widths and column starts (device rows are re-pitched to a
+    multiple of 8 samples so the vector-load path stays on): chunked == whole, for the three fast kernels."""
+    _torch()
+    import ctypes as C
+    from sameold_b200 import _lib
+    lib = _lib.load()
+    ns, n = 37, 9 * 22050 + 5
+    stride = n + 3
+    plans = synth.plan_corpus(ns, 22050, 9.0, first_stream=4242)
+    hptr = lib.same_host_alloc(ns * stride * 2)
+    assert hptr
+    try:
+        host = np.ctypeslib.as_array(C.cast(hptr, C.POINTER(C.c_int16)), shape=(ns, stride))
+        for s_, pl in enumerate(plans):
+            host[s_, :n] = synth.render_numpy(pl, n)
+        b = sb.SameReceiverBuilder.samedec(22050)
+        want = b.build_batch(ns).process([host[s_, :n].copy() for s_ in range(ns)])
+        assert sum(len(w) for w in want) > 100
+        for kernel in (2, 3, 4):
+            rx = b.build_batch(ns)
+            rx.set_option("kernel", kernel)
+            got = [[] for _ in range(ns)]
+            col = 0
+            for width in (1, 7, 55125, 33333, 22051, n):
+                w = min(width, n - col)
+                if w <= 0:
+                    break
+                rx.submit_2d(hptr, stride, col, w)
+                col += w
+                rx.sync()
+                for s_, e in enumerate(rx.drain_by_stream()):
+                    got[s_].extend(e)
+            assert col == n
+            for s_ in range(ns):
+                assert_events_equal(got[s_], want[s_], f"kernel {kernel} stream {s_} 2-D odd chunks")
+    finally:
+        lib.same_host_free(hptr)
+
+
+def test_truncated_burst_longer_than_the_engine_buffer():
+    """framing.rs:152-162 has no burst length cap; the engine keeps SAME_BURST_CAP = 1024 bytes and says so
+    (SAME_EV_FLAG_TRUNCATED, data_len = true length).  Everything else -- sample indices, the transport layer, which
+    only reads 268 bytes (assembler.rs:169) -- must still match the oracle."""
+    _torch()
+    text = b"ZCZC-" + (b"ABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789-+/ " * 40)[:1500]
+    plan = synth.StreamPlan("", [11025.0], [synth.PREAMBLE + text], 1.5, 99)
+    n = int(30 * 22050)
+    x = synth.render_numpy(plan, n, noise_sigma=200.0)
+    b = sb.SameReceiverBuilder.samedec(22050)
+    o = Oracle(oracle_cfg_from(b))
+    o.process_s16(x)
+    want = o.events()
+    wb = [e for e in want if e.kind == 3]
+    assert len(wb) == 1 and len(wb[0].data) > 1400
+    for kernel in (0, 1, 2, 4):
+        rx = b.build_batch(1)
+        rx.set_option("kernel", kernel)
+        rx.submit([x]); rx.sync()
+        evs, pay = rx.drain_raw()
+        got = sb.SameBatchReceiver.events_from_raw(evs, pay)
+        assert len(got) == len(want)
+        for g, w, r in zip(got, want, evs):
+            assert (g.kind, g.err, g.sample, g.symbol_count) == (w.kind, w.err, w.sample, w.symbol_count)
+            if g.kind == 3:
+                assert int(r["data_len"]) == len(w.data) and (g.flags & 1) and g.data == w.data[:1024]
+            else:
+                assert g.data == w.data and g.flags == 0
+
+
+def test_multi_device_entry_two_shards_equal_one_engine():
+    """same_multi_*: one batch over several engines, one host thread each (here both shards on device 0; all visible
+    devices too when the box has more).  Results == a single engine, global stream ids, sorted."""
+    torch = _torch()
+    ns = 75
+    recs = [synth.render_numpy(synth.plan_stream(2000 + i, seconds=14.0), 14 * 22050 - 31 * i) for i in range(ns)]
+    recs[3] = recs[3][:0]
+    b = sb.SameReceiverBuilder.samedec(22050)
+    want = b.build_batch(ns).process(recs)
+    layouts = [[0, 0], [0, 0, 0]]
+    if torch.cuda.device_count() > 1:
+        layouts.append(list(range(torch.cuda.device_count())))
+    for devices in layouts:
+        rx = b.build_multi(ns, devices)
+        sh = rx.shards()
+        assert sh[0][1] == 0 and sum(c for _, _, c in sh) == ns and all(sh[i][1] + sh[i][2] == sh[i + 1][1] for i in range(len(sh) - 1))
+        half = [r[: len(r) // 2] for r in recs]
+        rest = [r[len(r) // 2:] for r in recs]
+        got = rx.process(half)
+        for s_, e in enumerate(rx.process(rest)):
+            got[s_].extend(e)
+        for s_ in range(ns):
+            assert_events_equal(got[s_], want[s_], f"devices {devices} stream {s_}")
+        assert np.array_equal(rx.input_sample_counters(), np.array([len(r) for r in recs], np.uint64))
+        msgs = list(b.build_multi(ns, devices).iter_messages_batched(recs))
+        assert msgs == [(s_, e.message_ok()) for s_ in range(ns) for e in want[s_] if e.message_ok() is not None]
+        rx.reset()
+        assert not rx.input_sample_counters().any()
+
+
+def test_kernel_policy_crossovers_are_pinned():
+    """The engine picks its kernel from the batch size (same_engine.cu, measured table in profiles/README.md); a change
+    of the thresholds must be a deliberate one."""
+    _torch()
+    b = sb.SameReceiverBuilder.samedec(22050)
+    for ns, want in POLICY_TABLE:
+        rx = b.build_batch(ns)
+        assert rx.get_option("kernel_selected") == want, (ns, rx.get_option("kernel_selected"), want)
+        del rx
+    assert sb.SameReceiverBuilder.samedec(44100).build_batch(64).get_option("kernel_selected") == 1
+
+
+# (streams, kernel): 3 pipelined up to one 32-stream block per SM (148 SMs), 4 three-warp up to four, 2 single-warp beyond
+POLICY_TABLE = [(1, 3), (4096, 3), (4736, 3), (4737, 4), (8192, 4), (18944, 4), (18945, 2), (32768, 2)]

@@ -70,3 +70,48 @@ def test_two_rank_gloo_decode_and_gather(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "SHARD_OK 2" in out.stdout
+
+
+GPU_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["SAME_ROOT"])
+import torch, torch.distributed as dist
+import sameold_b200 as sb
+from oracle import load_golden_recording
+from sameold_b200.shard import decode_sharded
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+device = rank % torch.cuda.device_count()        # one engine per rank; ranks share a GPU when the box has fewer
+
+def decode_local(recs):
+    rx = sb.SameReceiverBuilder.samedec(22050).build_batch(len(recs), device=device)
+    return rx.decode_samedec(recs)
+
+names = ["long_message", "npt", "two_and_two", "npt", "two_and_two"]
+recs = [load_golden_recording(n) for n in names]
+res = decode_sharded(recs, decode_local, rank, world)
+expected = {}
+for n in set(names):
+    with open(os.path.join(os.environ["SAME_ROOT"], "tests", "golden", f"{n}.22050.s16le.txt")) as f:
+        expected[n] = [l.rstrip("\n") for l in f if not l.startswith("+OK")]
+assert res == [expected[n] for n in names], (rank, res)
+dist.barrier()
+if rank == 0:
+    print("GPU_SHARD_OK", world)
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.gpu
+def test_two_rank_decode_sharded_with_the_gpu_engine(tmp_path):
+    """decode_sharded over two processes, each with its own CUDA engine (SameBatchReceiver.decode_samedec): the
+    multi-process host path bench.py's torchrun launch uses, with the product decoder instead of the oracle."""
+    script = tmp_path / "gpu_worker.py"
+    script.write_text(GPU_WORKER)
+    env = dict(os.environ, SAME_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29613", str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "GPU_SHARD_OK 2" in out.stdout
