@@ -139,6 +139,8 @@ extern "C" {
     pub fn same_engine_read_soft_trace(e: *mut same_engine, stream: u32, out: *mut same_soft_symbol, cap: usize, n: *mut usize) -> c_int;
     pub fn same_engine_set_option(e: *mut same_engine, key: *const c_char, value: c_int) -> c_int;
     pub fn same_engine_get_option(e: *mut same_engine, key: *const c_char, value: *mut c_int) -> c_int;
+    pub fn same_engine_frontend_probe(e: *mut same_engine, d_samples: *const i16, total_samples: u64, offsets: *const u64,
+                                      lengths: *const u32, reps: c_int, ms_per_launch: *mut f32) -> c_int;
     pub fn same_engine_last_timing(e: *mut same_engine, h2d_ms: *mut f32, kernel_ms: *mut f32) -> c_int;
     pub fn same_engine_launch_count(e: *const same_engine) -> u64;
     pub fn same_engine_timer_start(e: *mut same_engine) -> c_int;

@@ -195,7 +195,10 @@ int same_engine_read_soft_trace(same_engine* e, uint32_t stream, same_soft_symbo
  * reads no environment variables: this call is the only way to override the measured kernel policy.
  *   "kernel"          0 engine picks the kernel from the batch size (default); 1 rate-generic kernel even where the
  *                     22050 Hz fast kernels apply; 2 single-warp fast kernel; 3 four-warp pipelined kernel;
- *                     4 three-warp kernel.  ("force_generic" is the old name of the same option.)
+ *                     4 three-warp kernel; 5 split pipeline: the time-parallel front-end kernel (s16 -> exact DC-blocked
+ *                     f32 tiles, HBM-bound) followed by the single-warp kernel fed from those tiles -- the measured
+ *                     alternative to the fused kernels.  ("force_generic": old name.)
+ *   "fast_variant"    single-warp kernel's window ring: 0 with mirror slots (default), 1 without (more resident warps)
  *   "lanes_per_warp"  streams per warp of the fast kernels (1, 2, 4, 8, 16, 32)
  *   "device_sort"     1 (default): big batches of events are put into per-stream order on the device before the
  *                     read-back; 0: always on the host
@@ -205,6 +208,11 @@ int same_engine_set_option(same_engine* e, const char* key, int value);
  * 2 single-warp, 3 pipelined, 4 three-warp) — the policy result for this batch size unless "kernel" overrides it. */
 int same_engine_get_option(same_engine* e, const char* key, int* value);
 
+/* Measurement aid: runs only the front-end kernel (feed-forward stages: s16 -> f32, DC blocker; 2 B read + 4 B written
+ * per sample) `reps` times on device-resident samples and returns its CUDA-event time per launch.  The resident
+ * receiver state is not changed. */
+int same_engine_frontend_probe(same_engine* e, const int16_t* d_samples, uint64_t total_samples, const uint64_t* offsets,
+                               const uint32_t* lengths, int reps, float* ms_per_launch);
 /* Timing of the last completed submit, measured with CUDA events on the engine's stream: host->device copy and
  * receiver kernel, in milliseconds; kernel launch count since create (for bench.py's gpu_launches). */
 int same_engine_last_timing(same_engine* e, float* h2d_ms, float* kernel_ms);

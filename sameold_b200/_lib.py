@@ -87,6 +87,7 @@ API = {
     "same_engine_read_soft_trace": (C.c_int, [_P, C.c_uint32, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "same_engine_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "same_engine_get_option": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int)]),
+    "same_engine_frontend_probe": (C.c_int, [_P, _P, C.c_uint64, _P, _P, C.c_int, C.POINTER(C.c_float)]),
     "same_engine_last_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "same_engine_launch_count": (C.c_uint64, [_P]),
     "same_engine_timer_start": (C.c_int, [_P]),

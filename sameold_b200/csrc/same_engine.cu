@@ -19,7 +19,9 @@
 extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps, const SameTaps2* taps2, int force_generic,
                                       uint32_t lanes_per_warp, const void* d_samples, int sample_fmt,
                                       const unsigned long long* d_offsets, const uint32_t* d_lengths,
-                                      cudaStream_t stream);
+                                      const SameTiles* tiles, int fast_variant, cudaStream_t stream);
+extern "C" cudaError_t same_launch_frontend(const SameParams* p, const int16_t* d_samples, const unsigned long long* d_offsets,
+                                            const uint32_t* d_lengths, const SameTiles* tiles, cudaStream_t stream);
 extern "C" cudaError_t same_launch_evsort(const same_event* d_events, uint32_t n, uint32_t n_streams, uint32_t* d_cnt,
                                           uint32_t* d_minseq, uint32_t* d_start, same_event* d_sorted, uint32_t* d_bad,
                                           cudaStream_t stream);
@@ -83,6 +85,9 @@ struct same_engine {
   uint32_t lanes_per_warp = 32;   // streams per warp in the fast kernel (lane-sparse warps for small batches)
   int sm_count = 148;
   int kernel_auto = 0;            // fast-kernel flavour when force_generic == 0: 3 pipelined, 4 three-warp, 2 single-warp
+  int fast_variant = 0;           // option "fast_variant": y ring of the single-warp kernel with (0) / without (1) mirror slots
+  SameTiles tiles{nullptr, nullptr, 0u};   // split pipeline (kernel 5): front-end output, allocated on first use
+  size_t tiles_cap = 0;           // floats
   bool saw_f32 = false;           // an f32 submit happened since create / reset(all): DC state may be non-integer -> generic kernel
   uint64_t lost_events = 0, lost_payloads = 0;
   same_derived derived;
@@ -233,6 +238,21 @@ int ensure_input(same_engine* e, InputBuf& b, size_t bytes) {
   return SAME_OK;
 }
 
+// Tile buffer of the split pipeline: n_pad streams x n_max samples of f32 (+ the 34-word DC state per stream).
+int ensure_tiles(same_engine* e, uint32_t max_len) {
+  const uint32_t n_max = (max_len + 31u) & ~31u;
+  const size_t need = (size_t)e->p.layout.n_pad * n_max;
+  if (need > e->tiles_cap) {
+    if (e->tiles.d) CK(e, cudaFree(e->tiles.d));
+    e->tiles.d = nullptr; e->tiles_cap = 0;
+    CK(e, cudaMalloc(&e->tiles.d, need * sizeof(float)));
+    e->tiles_cap = need;
+  }
+  if (!e->tiles.dc_next) CK(e, cudaMalloc(&e->tiles.dc_next, (size_t)34 * e->p.layout.n_pad * sizeof(uint32_t)));
+  e->tiles.n_max = n_max;
+  return SAME_OK;
+}
+
 struct Submit2D { uint64_t row_stride = 0, col_start = 0, dpitch = 0; uint32_t n_cols = 0; bool on = false; };
 
 // sample_fmt: 0 = int16, 1 = float32
@@ -296,8 +316,21 @@ int submit_common(same_engine* e, const void* host_samples, const void* dev_samp
   CK(e, cudaStreamWaitEvent(e->compute, b.copied, 0));
   CK(e, cudaEventRecord(e->t_k0, e->compute));
   // f32 input (now or earlier: the DC-blocker state may hold non-integers) needs the literal f32 recursion
-  const int kernel = e->saw_f32 ? 1 : (e->force_generic ? e->force_generic : e->kernel_auto);
-  CK(e, same_launch_rx(&e->p, &e->taps, &e->taps2, kernel, e->lanes_per_warp, d_src, sample_fmt, b.d_off, b.d_len, e->compute));
+  int kernel = e->saw_f32 ? 1 : (e->force_generic ? e->force_generic : e->kernel_auto);
+  if (kernel == 5) {
+    // split pipeline: the front end needs real samples (a zeros submit has none: the fused single-warp kernel takes it,
+    // the resident state is the same) and a tile buffer for the longest chunk
+    if (zeros || !d_src) kernel = 2;
+    else {
+      uint32_t max_len = 0;
+      for (uint32_t i = 0; i < e->n_streams; ++i) max_len = std::max(max_len, lengths[i]);
+      int rc = ensure_tiles(e, max_len);
+      if (rc) return rc;
+      e->launches += 1;   // the front-end kernel
+    }
+  }
+  CK(e, same_launch_rx(&e->p, &e->taps, &e->taps2, kernel, e->lanes_per_warp, d_src, sample_fmt, b.d_off, b.d_len, &e->tiles,
+                       e->fast_variant, e->compute));
   CK(e, cudaEventRecord(e->t_k1, e->compute));
   CK(e, cudaEventRecord(b.consumed, e->compute));
   b.used = true;
@@ -531,6 +564,8 @@ void same_engine_destroy(same_engine* e) {
   for (auto& ev : e->stage_done) if (ev) cudaEventDestroy(ev);
   if (e->d_trace) cudaFree(e->d_trace);
   if (e->d_ids) cudaFree(e->d_ids);
+  if (e->tiles.d) cudaFree(e->tiles.d);
+  if (e->tiles.dc_next) cudaFree(e->tiles.dc_next);
   for (cudaEvent_t ev : {e->t_h2d0, e->t_h2d1, e->t_k0, e->t_k1, e->t_sw0, e->t_sw1}) if (ev) cudaEventDestroy(ev);
   if (e->compute) cudaStreamDestroy(e->compute);
   if (e->copy) cudaStreamDestroy(e->copy);
@@ -775,8 +810,13 @@ int same_engine_set_option(same_engine* e, const char* key, int value) {
   int rc = same_engine_sync(e);
   if (rc) return rc;
   if (strcmp(key, "kernel") == 0 || strcmp(key, "force_generic") == 0) {
-    if (value < 0 || value > 4) return fail(e, SAME_ERR_INVALID_ARG, "kernel must be 0 (policy), 1 generic, 2 single-warp, 3 pipelined or 4 three-warp");
+    if (value < 0 || value > 5) return fail(e, SAME_ERR_INVALID_ARG, "kernel must be 0 (policy), 1 generic, 2 single-warp, 3 pipelined, 4 three-warp or 5 split (front end + tile-fed)");
     e->force_generic = value;
+    return SAME_OK;
+  }
+  if (strcmp(key, "fast_variant") == 0) {
+    if (value < 0 || value > 1) return fail(e, SAME_ERR_INVALID_ARG, "fast_variant must be 0 or 1");
+    e->fast_variant = value;
     return SAME_OK;
   }
   if (strcmp(key, "device_sort") == 0) { e->device_sort = value != 0; return SAME_OK; }
@@ -794,12 +834,41 @@ int same_engine_get_option(same_engine* e, const char* key, int* value) {
   if (strcmp(key, "kernel") == 0 || strcmp(key, "force_generic") == 0) { *value = e->force_generic; return SAME_OK; }
   if (strcmp(key, "device_sort") == 0) { *value = e->device_sort; return SAME_OK; }
   if (strcmp(key, "lanes_per_warp") == 0) { *value = (int)e->lanes_per_warp; return SAME_OK; }
+  if (strcmp(key, "fast_variant") == 0) { *value = e->fast_variant; return SAME_OK; }
   if (strcmp(key, "kernel_selected") == 0) {
     const bool fast_geometry = e->p.ntaps == 42 && e->p.dc_len == 16;
     *value = (e->saw_f32 || !fast_geometry) ? 1 : (e->force_generic ? e->force_generic : e->kernel_auto);
     return SAME_OK;
   }
   return fail(e, SAME_ERR_INVALID_ARG, std::string("unknown option ") + key);
+}
+
+int same_engine_frontend_probe(same_engine* e, const int16_t* d_samples, uint64_t total_samples, const uint64_t* offsets,
+                               const uint32_t* lengths, int reps, float* ms_per_launch) {
+  if (!e || !d_samples || !offsets || !lengths || !ms_per_launch || reps < 1) return fail(e, SAME_ERR_INVALID_ARG, "null argument");
+  if (e->p.ntaps != 42 || e->p.dc_len != 16) return fail(e, SAME_ERR_INVALID_CONFIG, "the front-end kernel is the 22050 Hz class (DC length 16)");
+  int rc = same_engine_sync(e);
+  if (rc) return rc;
+  uint32_t max_len = 0;
+  for (uint32_t i = 0; i < e->n_streams; ++i) {
+    if (lengths[i] && offsets[i] + lengths[i] > total_samples) return fail(e, SAME_ERR_INVALID_ARG, "offset+length exceeds total_samples");
+    max_len = std::max(max_len, lengths[i]);
+  }
+  rc = ensure_tiles(e, max_len);
+  if (rc) return rc;
+  InputBuf& b = e->in[0];
+  CK(e, cudaMemcpyAsync(b.d_off, offsets, e->n_streams * sizeof(uint64_t), cudaMemcpyHostToDevice, e->compute));
+  CK(e, cudaMemcpyAsync(b.d_len, lengths, e->n_streams * sizeof(uint32_t), cudaMemcpyHostToDevice, e->compute));
+  CK(e, same_launch_frontend(&e->p, d_samples, b.d_off, b.d_len, &e->tiles, e->compute));   // warm-up
+  CK(e, cudaEventRecord(e->t_k0, e->compute));
+  for (int i = 0; i < reps; ++i) CK(e, same_launch_frontend(&e->p, d_samples, b.d_off, b.d_len, &e->tiles, e->compute));
+  CK(e, cudaEventRecord(e->t_k1, e->compute));
+  CK(e, cudaStreamSynchronize(e->compute));
+  float ms = 0.0f;
+  CK(e, cudaEventElapsedTime(&ms, e->t_k0, e->t_k1));
+  *ms_per_launch = ms / (float)reps;
+  e->launches += (uint64_t)reps + 1;
+  return SAME_OK;
 }
 
 int same_engine_last_timing(same_engine* e, float* h2d_ms, float* kernel_ms) {

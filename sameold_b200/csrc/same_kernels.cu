@@ -199,13 +199,277 @@ __device__ __forceinline__ int s16_lo(uint32_t w) {   // sign-extended low half 
 __device__ __forceinline__ int s16_hi(uint32_t w) { return ((int)w) >> 16; }
 __device__ __forceinline__ int s16_at(const uint32_t* w, int i) { return (i & 1) ? s16_hi(w[i >> 1]) : s16_lo(w[i >> 1]); }
 
-__global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant__ SameParams p,
+// ----------------------------------------------------------------------------------------------------------------
+// Exact integer DC blocker (A0 + A1 for the 22050 Hz geometry), shared by every fast kernel and the front-end kernel.
+//
+// With s16 input and length 16 every intermediate of dcblock.rs:45-49,104-108 is an integer / 16 / 256 below 2^24, so
+// the f32 running sums have no rounding error and equal these integer recursions:
+//     S1 += x - x[-16]            ff: moving_sum += input - aged      dcblock.rs:106     (S1 = 16 * ma0)
+//     S2 += S1 - S1[-16]          fb: moving_sum += ma0 - aged        dcblock.rs:106     (S2 = 256 * ma1)
+//     d   = (256 * x[-15] - S2) / 256                                  dcblock.rs:48
+// State: the last 16 raw samples (packed pairs, oldest first) and the last 16 values of S1.  One chunk = 32 samples,
+// everything statically indexed (registers).
+// ----------------------------------------------------------------------------------------------------------------
+struct DcInt {
+  uint32_t rawh[FAST_DCL / 2];   // last 16 raw samples, packed pairs, oldest first   (ff window, dcblock.rs:63)
+  int s1h[FAST_DCL];             // S1 of the last 16 samples                         (fb window)
+  int S1, S2;
+};
+
+// word index of the DC state inside a 34-word block: ff window 0..15, fb window 16..31, ff sum 32, fb sum 33
+#define DCW_FF 0
+#define DCW_FB 16
+#define DCW_FFSUM 32
+#define DCW_FBSUM 33
+#define DCW_WORDS 34
+
+__device__ __forceinline__ void dc_load(DcInt& q, const uint32_t* st, const SameLayout& L) {
+  q.S1 = __float2int_rn(__uint_as_float(LANE_ST(st, L, F_DC_FFSUM)));              // ff moving_sum
+  q.S2 = __float2int_rn(__uint_as_float(LANE_ST(st, L, F_DC_FBSUM)) * 16.0f);      // 16 * fb moving_sum
+#pragma unroll
+  for (int i = 0; i < FAST_DCL / 2; ++i) {
+    const int lo = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_ff + 2 * i)));
+    const int hi = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_ff + 2 * i + 1)));
+    q.rawh[i] = ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16);
+  }
+#pragma unroll
+  for (int i = 0; i < FAST_DCL; ++i) q.s1h[i] = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_fb + i)) * 16.0f);
+}
+
+__device__ __forceinline__ void dc_zero(DcInt& q) {
+  q.S1 = 0; q.S2 = 0;
+#pragma unroll
+  for (int i = 0; i < FAST_DCL / 2; ++i) q.rawh[i] = 0u;
+#pragma unroll
+  for (int i = 0; i < FAST_DCL; ++i) q.s1h[i] = 0;
+}
+
+// One full chunk of 32 samples (packed pairs in cur); emit(i, d) receives the DC-blocked sample i as exact f32.
+template <class Emit>
+__device__ __forceinline__ void dc_chunk(DcInt& q, const uint32_t (&cur)[FAST_CHUNK / 2], Emit&& emit) {
+#pragma unroll
+  for (int i = 0; i < FAST_CHUNK; ++i) {
+    const int x = s16_at(cur, i);
+    const int x16 = (i < FAST_DCL) ? s16_at(q.rawh, i) : s16_at(cur, i - FAST_DCL);
+    const int x15 = (i < FAST_DCL - 1) ? s16_at(q.rawh, i + 1) : s16_at(cur, i - (FAST_DCL - 1));
+    q.S1 += x - x16;
+    q.S2 += q.S1 - q.s1h[i & 15];
+    q.s1h[i & 15] = q.S1;
+    const int D = (x15 << 8) - q.S2;
+    emit(i, (float)D * 0.00390625f);
+  }
+#pragma unroll
+  for (int i = 0; i < FAST_DCL / 2; ++i) q.rawh[i] = cur[FAST_CHUNK / 2 - FAST_DCL / 2 + i];
+}
+
+// The final, partial chunk of a submit (nnew < 32 samples; cur zero-filled beyond nnew).  The histories are NOT
+// rotated afterwards: dc_store_after_partial writes them out in canonical order.
+template <class Emit>
+__device__ __forceinline__ void dc_chunk_partial(DcInt& q, const uint32_t (&cur)[FAST_CHUNK / 2], const int nnew, Emit&& emit) {
+#pragma unroll
+  for (int i = 0; i < FAST_CHUNK; ++i) {
+    if (i < nnew) {
+      const int x = s16_at(cur, i);
+      const int x16 = (i < FAST_DCL) ? s16_at(q.rawh, i) : s16_at(cur, i - FAST_DCL);
+      const int x15 = (i < FAST_DCL - 1) ? s16_at(q.rawh, i + 1) : s16_at(cur, i - (FAST_DCL - 1));
+      q.S1 += x - x16;
+      q.S2 += q.S1 - q.s1h[i & 15];
+      q.s1h[i & 15] = q.S1;
+      const int D = (x15 << 8) - q.S2;
+      emit(i, (float)D * 0.00390625f);
+    }
+  }
+}
+
+// DC state out, canonical f32 form (the generic kernel's layout), through store(word, bits) with word in 0..33.
+// After whole chunks only: the histories are in order.
+template <class Store>
+__device__ __forceinline__ void dc_store(const DcInt& q, Store&& store) {
+  store(DCW_FFSUM, __float_as_uint((float)q.S1));
+  store(DCW_FBSUM, __float_as_uint((float)q.S2 * 0.0625f));
+#pragma unroll
+  for (int i = 0; i < FAST_DCL; ++i) {
+    store(DCW_FF + i, __float_as_uint((float)s16_at(q.rawh, i)));
+    store(DCW_FB + i, __float_as_uint((float)q.s1h[i] * 0.0625f));
+  }
+}
+// After a partial chunk of nnew samples: rotate so that index 0 is the oldest sample again (static register indices,
+// run-time word numbers -- no dynamically indexed register arrays).  The last 16 samples are old-history entries
+// i >= nnew and chunk samples nnew-16 <= i < nnew; the S1 of chunk sample j lives in s1h[j & 15].
+template <class Store>
+__device__ __forceinline__ void dc_store_after_partial(const DcInt& q, const uint32_t (&cur)[FAST_CHUNK / 2], const uint32_t nnew,
+                                                       Store&& store) {
+  store(DCW_FFSUM, __float_as_uint((float)q.S1));
+  store(DCW_FBSUM, __float_as_uint((float)q.S2 * 0.0625f));
+#pragma unroll
+  for (int i = 0; i < FAST_DCL; ++i) {
+    if (i >= (int)nnew) store(DCW_FF + ((uint32_t)i - nnew), __float_as_uint((float)s16_at(q.rawh, i)));
+    store(DCW_FB + (((uint32_t)i - nnew) & 15u), __float_as_uint((float)q.s1h[i] * 0.0625f));
+  }
+#pragma unroll
+  for (int i = 0; i < FAST_CHUNK; ++i) {
+    if (i < (int)nnew && i + FAST_DCL >= (int)nnew)
+      store(DCW_FF + ((uint32_t)(i + FAST_DCL) - nnew), __float_as_uint((float)s16_at(cur, i)));
+  }
+}
+// store target: the resident state words of this lane
+struct DcToState {
+  uint32_t* st; const SameLayout& L;
+  __device__ __forceinline__ void operator()(uint32_t w, uint32_t bits) const {
+    const uint32_t word = w < DCW_FB ? L.dc_ff + w : w < DCW_FFSUM ? L.dc_fb + (w - DCW_FB) : (w == DCW_FFSUM ? (uint32_t)F_DC_FFSUM : (uint32_t)F_DC_FBSUM);
+    LANE_ST(st, L, word) = bits;
+  }
+};
+
+// Raw-sample feed of one lane: 32-sample chunks as packed pairs, four 16-byte loads per chunk issued one chunk
+// ahead (a refill happens at most once per round, so the global-load latency overlaps a round of sequential work).
+struct RawFeed {
+  const int16_t* src;
+  int4 nx[4];
+  bool aligned, pf_ok;
+  __device__ __forceinline__ void init(const int16_t* s, uint32_t first, uint32_t len) {
+    src = s;
+    aligned = (reinterpret_cast<uintptr_t>(s) & 15u) == 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) nx[i] = make_int4(0, 0, 0, 0);
+    pf_ok = src != nullptr && aligned && first + (uint32_t)FAST_CHUNK <= len;
+    if (pf_ok) {
+      const int4* q = reinterpret_cast<const int4*>(src + first);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) nx[i] = __ldg(q + i);
+    }
+  }
+  // the full chunk at rp (rp % 8 == 0 relative to an aligned src); prefetches the chunk after it
+  __device__ __forceinline__ void take_full(uint32_t (&cur)[FAST_CHUNK / 2], uint32_t rp, uint32_t len) {
+    if (pf_ok) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { cur[4 * i] = nx[i].x; cur[4 * i + 1] = nx[i].y; cur[4 * i + 2] = nx[i].z; cur[4 * i + 3] = nx[i].w; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < FAST_CHUNK / 2; ++i) {
+        const uint32_t lo = src ? (uint32_t)(uint16_t)src[rp + 2 * i] : 0u;
+        const uint32_t hi = src ? (uint32_t)(uint16_t)src[rp + 2 * i + 1] : 0u;
+        cur[i] = lo | (hi << 16);
+      }
+    }
+    pf_ok = src != nullptr && aligned && (len - rp) >= 2u * FAST_CHUNK;
+    if (pf_ok) {
+      const int4* q = reinterpret_cast<const int4*>(src + rp + FAST_CHUNK);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) nx[i] = __ldg(q + i);
+    }
+  }
+  // a partial chunk of nnew < 32 samples at rp: scalar loads, zero-filled
+  __device__ __forceinline__ void take_partial(uint32_t (&cur)[FAST_CHUNK / 2], uint32_t rp, uint32_t nnew) const {
+#pragma unroll
+    for (int i = 0; i < FAST_CHUNK / 2; ++i) cur[i] = 0u;
+#pragma unroll
+    for (int i = 0; i < FAST_CHUNK; ++i) {
+      const uint32_t v = (src && i < (int)nnew) ? (uint32_t)(uint16_t)src[rp + i] : 0u;
+      cur[i >> 1] |= (i & 1) ? (v << 16) : v;
+    }
+  }
+};
+
+// One AGC step (agc.rs:72-77): y = x*g; g += (!locked as f32)*(1-|y|)*bw; g = clamp(g, min, max).  `bw_eff` is bw or 0.
+__device__ __forceinline__ float agc_step(float& g, const float d, const float bw_eff, const float gmin, const float gmax) {
+  const float y = FMUL(d, g);                                                       // agc.rs:73
+  g = fminf(fmaxf(FADD(g, FMUL(FSUB(1.0f, fabsf(y)), bw_eff)), gmin), gmax);        // agc.rs:74-75
+  return y;
+}
+
+// AGC over one lane's segment of the d ring into the y ring (A2, A3), shared by the single-warp and three-warp kernels.
+// Every lane runs the warp's longest trip count.  Samples k0 .. nmin-1 (nmin = warp minimum) need no predicate; in the
+// short tail, samples beyond a lane's own segment use bandwidth 0 (g + t*0 == g exactly; the stale d they read is
+// finite) and store nothing.  The d loads of a group are issued together so that their latency is paid once per group.
+// od / oy: byte offsets ((slot * 128) | lane * 4) of sample k0 in the d ring (mask DMASK) and the y ring (64 slots;
+// MIRROR: each y is stored at slot j and at its mirror j + 64).
+template <uint32_t DMASK, bool MIRROR>
+__device__ __forceinline__ float agc_segment(float g, const float bw_eff, const float gmin, const float gmax,
+                                             const uint32_t d_base, const uint32_t y_base, uint32_t od, uint32_t oy, int k,
+                                             const int nmin, const int maxseg, const int nseg) {
+  constexpr bool ONE = (DMASK == 0x1fffu);   // d ring and y ring of the same size: one running offset serves both
+  for (; k + 4 <= nmin; k += 4) {
+    float dv[4]; uint32_t oo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      oo[j] = oy; dv[j] = lds_f32(d_base + (ONE ? oy : od));
+      if (!ONE) od = (od + 128u) & DMASK;
+      oy = (oy + 128u) & 0x1fffu;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float y = agc_step(g, dv[j], bw_eff, gmin, gmax);
+      if (MIRROR) sts_f32_mirrored(y_base + oo[j], y); else sts_f32(y_base + oo[j], y);    // demod.rs:177-179
+    }
+  }
+  for (; k < maxseg; k += 2) {
+    float dv[2]; uint32_t oo[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      oo[j] = oy; dv[j] = lds_f32(d_base + (ONE ? oy : od));
+      if (!ONE) od = (od + 128u) & DMASK;
+      oy = (oy + 128u) & 0x1fffu;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const bool act = (k + j) < nseg;
+      const float y = agc_step(g, dv[j], act ? bw_eff : 0.0f, gmin, gmax);
+      if (act) { if (MIRROR) sts_f32_mirrored(y_base + oo[j], y); else sts_f32(y_base + oo[j], y); }
+    }
+  }
+  return g;
+}
+
+// Matched filters (A4) at the sample that ends at ring position `end` (exclusive), packed exact f32 ops:
+// fma(v, h, -0) == RN(v*h) and fma(acc, 1, prod) == RN(acc + prod): two separately rounded operations per tap and
+// accumulator, as filter.rs:363-377 requires.  The -0 and 1 operands are run-time values (SameParams) so that ptxas
+// cannot fold the pair back into one fused multiply-add.  MIRROR: the window is read at descending static offsets
+// from its newest slot (never wraps); otherwise every tap address is wrapped into the 64-slot ring.
+template <bool MIRROR>
+__device__ __forceinline__ float mf_soft(const float* yring, const float4* tapsm, const int lane, const uint32_t end,
+                                         const float2 one2, const float2 negz2) {
+  float2 am = make_float2(0.0f, 0.0f), as = make_float2(0.0f, 0.0f);
+  if (MIRROR) {
+    int nslot = (int)((end - 1u) & (FAST_RING - 1));
+    if (nslot < FAST_NTAPS - 1) nslot += FAST_RING;
+    const float* yp = yring + nslot * 32 + lane;
+#pragma unroll
+    for (int i = 0; i < FAST_NTAPS; ++i) {
+      const float v = yp[-i * 32];
+      const float4 t = tapsm[i];
+      const float2 vv = make_float2(v, v);
+      am = __ffma2_rn(am, one2, __ffma2_rn(vv, make_float2(t.x, t.y), negz2));
+      as = __ffma2_rn(as, one2, __ffma2_rn(vv, make_float2(t.z, t.w), negz2));
+    }
+  } else {
+    const uint32_t y_lane = smem_u32(yring) + ((uint32_t)lane << 2);
+    const uint32_t e = ((end - 1u) & (FAST_RING - 1)) << 7;
+#pragma unroll
+    for (int i = 0; i < FAST_NTAPS; ++i) {
+      const float v = lds_f32(y_lane + ((e - (uint32_t)(i << 7)) & 0x1f80u));
+      const float4 t = tapsm[i];
+      const float2 vv = make_float2(v, v);
+      am = __ffma2_rn(am, one2, __ffma2_rn(vv, make_float2(t.x, t.y), negz2));
+      as = __ffma2_rn(as, one2, __ffma2_rn(vv, make_float2(t.z, t.w), negz2));
+    }
+  }
+  return rclamp(FSUB(hypot_fixed(am.x, am.y), hypot_fixed(as.x, as.y)), -1.0f, 1.0f);  // demod.rs:163
+}
+
+// TILE_FED: the DC-blocked samples come from same_frontend_kernel's lane-major f32 tiles instead of the fused integer
+// recursion (measured A/B of DESIGN.md §5; the kernel then only commits the front end's DC state).
+// MIRROR: y ring with mirror slots (static matched-filter addresses, 2 stores per sample, 16 KB) or without (8 KB,
+// wrapped addresses): smaller shared memory -> more resident warps.
+template <bool TILE_FED, bool MIRROR, int MIN_BLOCKS>
+__global__ void __launch_bounds__(32, MIN_BLOCKS) same_rx_fast_kernel(const __grid_constant__ SameParams p,
                                                           const __grid_constant__ SameTaps2 taps,
                                                           const int16_t* __restrict__ samples,
                                                           const unsigned long long* __restrict__ offsets,
-                                                          const uint32_t* __restrict__ lengths, const uint32_t lanes) {
+                                                          const uint32_t* __restrict__ lengths, const uint32_t lanes,
+                                                          const SameTiles tiles) {
   __shared__ float dring[FAST_RING * 32];
-  __shared__ float yring[2 * FAST_RING * 32];
+  __shared__ float yring[(MIRROR ? 2 : 1) * FAST_RING * 32];
   __shared__ float4 tapsm[FAST_NTAPS];
 
   const SameLayout& L = p.layout;
@@ -218,32 +482,27 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
 
   const uint32_t len = valid ? lengths[s] : 0u;
   if (__all_sync(0xffffffffu, len == 0u)) return;
-  const int16_t* src = (samples != nullptr && valid) ? samples + offsets[s] : nullptr;
-  const bool src_aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+  const int16_t* src = (!TILE_FED && samples != nullptr && valid) ? samples + offsets[s] : nullptr;
+  // tile-fed: sample n of this lane is tiles.d[(tile * n_max + n) * 32 + lane] (lanes == 32 only)
+  const float* tsrc = TILE_FED ? tiles.d + (size_t)blockIdx.x * tiles.n_max * 32u + (uint32_t)lane : nullptr;
 
   Lane a;
   lane_load(a, p, st, s);
 
-  // ---- DC blocker state as integers (exact: all values are integers / 16 / 256 for s16 input) ----
-  uint32_t rawh[FAST_DCL / 2];   // last 16 raw samples, packed pairs, oldest first   (ff window, dcblock.rs:63)
-  int s1h[FAST_DCL];             // S1 = 16 * ma0 for the last 16 samples            (fb window)
-  int S1 = __float2int_rn(__uint_as_float(LANE_ST(st, L, F_DC_FFSUM)));              // ff moving_sum
-  int S2 = __float2int_rn(__uint_as_float(LANE_ST(st, L, F_DC_FBSUM)) * 16.0f);      // 16 * fb moving_sum
-#pragma unroll
-  for (int i = 0; i < FAST_DCL / 2; ++i) {
-    int lo = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_ff + 2 * i)));
-    int hi = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_ff + 2 * i + 1)));
-    rawh[i] = ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16);
+  DcInt dc;
+  RawFeed feed;
+  if (!TILE_FED) {
+    dc_load(dc, st, L);
+    feed.init(src, 0u, len);
   }
-#pragma unroll
-  for (int i = 0; i < FAST_DCL; ++i) s1h[i] = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_fb + i)) * 16.0f);
   // demod window -> y ring slots of samples -42..-1 (and mirrors); d ring starts finite (stale slots are read, never used)
   for (int i = 0; i < FAST_RING; ++i) dring[i * 32 + lane] = 0.0f;
+  if (!MIRROR) for (int i = 0; i < FAST_RING; ++i) yring[i * 32 + lane] = 0.0f;
   for (int i = 0; i < FAST_NTAPS; ++i) {
     const float v = __uint_as_float(LANE_ST(st, L, L.win + i));
     const int slot = (i - FAST_NTAPS) & (FAST_RING - 1);
     yring[slot * 32 + lane] = v;
-    yring[(slot + FAST_RING) * 32 + lane] = v;
+    if (MIRROR) yring[(slot + FAST_RING) * 32 + lane] = v;
   }
   for (int i = lane; i < FAST_NTAPS; i += 32)
     tapsm[i] = make_float4(taps.mark[i].x, taps.mark[i].y, taps.space[i].x, taps.space[i].y);
@@ -254,7 +513,7 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
   const uint32_t d_base = smem_u32(dring), y_base = smem_u32(yring);
 
   uint32_t pos = 0;   // samples consumed by the AGC/TED side
-  uint32_t rp = 0;    // samples produced into the d ring (multiple of 16 except after the final partial chunk)
+  uint32_t rp = 0;    // samples produced into the d ring (multiple of 32 except after the final partial chunk)
   bool dc_windows_stored = false;
   int cfire = fire_clock(a.until, a.clock);
   // Byte-phase alignment: a lane whose squelch hands out a byte parks (consumes nothing) until the next round whose
@@ -269,18 +528,6 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
   uint32_t pend = 0;       // SYM_BYTE_READY | SYM_ADJUSTED while parked
   uint32_t round_ctr = 0;
 
-  // software prefetch of the next full 32-sample chunk (four 16-byte loads): issued one refill ahead, and a refill
-  // happens at most once per round, so the global-load latency overlaps a whole round of the sequential work
-  int4 nx[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) nx[i] = make_int4(0, 0, 0, 0);
-  bool pf_ok = src != nullptr && src_aligned && len >= (uint32_t)FAST_CHUNK;
-  if (pf_ok) {
-    const int4* q = reinterpret_cast<const int4*>(src);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) nx[i] = __ldg(q + i);
-  }
-
   while (__any_sync(0xffffffffu, pos < len || pend != 0u)) {
     round_ctr += 1;
     const bool byte_round = (round_ctr & 15u) == 0u;
@@ -290,80 +537,30 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
     while (__any_sync(0xffffffffu, (rp - pos) < 24u && rp < len && pend == 0u)) {
       const bool take = (rp < len) && (rp - pos) <= (uint32_t)(FAST_RING - FAST_CHUNK);
       const uint32_t nnew = take ? min((uint32_t)FAST_CHUNK, len - rp) : 0u;
-      if (nnew == FAST_CHUNK) {
+      float* dst = dring + (rp & (FAST_RING - 1)) * 32 + lane;  // rp % 32 == 0: the chunk never wraps
+      if (TILE_FED) {
+        if (nnew) {
+          const float* q = tsrc + (size_t)rp * 32u;
+          float v[FAST_CHUNK];
+#pragma unroll
+          for (int i = 0; i < FAST_CHUNK; ++i) v[i] = (i < (int)nnew) ? __ldg(q + i * 32) : 0.0f;
+#pragma unroll
+          for (int i = 0; i < FAST_CHUNK; ++i) dst[i * 32] = v[i];
+          rp += nnew;
+        }
+      } else if (nnew == FAST_CHUNK) {
         // ---- full chunk: everything static, no per-sample predicates ----
         uint32_t cur[FAST_CHUNK / 2];
-        if (pf_ok) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { cur[4 * i] = nx[i].x; cur[4 * i + 1] = nx[i].y; cur[4 * i + 2] = nx[i].z; cur[4 * i + 3] = nx[i].w; }
-        } else {
-#pragma unroll
-          for (int i = 0; i < FAST_CHUNK / 2; ++i) {
-            const uint32_t lo = src ? (uint32_t)(uint16_t)src[rp + 2 * i] : 0u;
-            const uint32_t hi = src ? (uint32_t)(uint16_t)src[rp + 2 * i + 1] : 0u;
-            cur[i] = lo | (hi << 16);
-          }
-        }
-        // prefetch the chunk after this one
-        pf_ok = src != nullptr && src_aligned && (len - rp) >= 2u * FAST_CHUNK;
-        if (pf_ok) {
-          const int4* q = reinterpret_cast<const int4*>(src + rp + FAST_CHUNK);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) nx[i] = __ldg(q + i);
-        }
-        float* dst = dring + (rp & (FAST_RING - 1)) * 32 + lane;  // rp % 32 == 0: the chunk never wraps
-#pragma unroll
-        for (int i = 0; i < FAST_CHUNK; ++i) {
-          const int x = s16_at(cur, i);
-          const int x16 = (i < FAST_DCL) ? s16_at(rawh, i) : s16_at(cur, i - FAST_DCL);
-          const int x15 = (i < FAST_DCL - 1) ? s16_at(rawh, i + 1) : s16_at(cur, i - (FAST_DCL - 1));
-          S1 += x - x16;                    // ff: moving_sum += input - aged          dcblock.rs:106
-          S2 += S1 - s1h[i & 15];           // fb: moving_sum += ma0 - aged            dcblock.rs:106
-          s1h[i & 15] = S1;
-          const int D = (x15 << 8) - S2;    // 256 * (sig - ma1)                       dcblock.rs:48
-          dst[i * 32] = (float)D * 0.00390625f;
-        }
-#pragma unroll
-        for (int i = 0; i < FAST_DCL / 2; ++i) rawh[i] = cur[FAST_CHUNK / 2 - FAST_DCL / 2 + i];
+        feed.take_full(cur, rp, len);
+        dc_chunk(dc, cur, [&](int i, float d) { dst[i * 32] = d; });
         rp += FAST_CHUNK;
       } else if (nnew) {
-        // ---- final partial chunk of this submit (rp reaches len): scalar loads, per-sample predicates ----
+        // ---- final partial chunk of this submit (rp reaches len): scalar loads, per-sample predicates; the DC
+        // windows are final now and are stored right here, rotated back into canonical order ----
         uint32_t cur[FAST_CHUNK / 2];
-#pragma unroll
-        for (int i = 0; i < FAST_CHUNK / 2; ++i) cur[i] = 0u;
-#pragma unroll
-        for (int i = 0; i < FAST_CHUNK; ++i) {
-          const uint32_t v = (src && i < (int)nnew) ? (uint32_t)(uint16_t)src[rp + i] : 0u;
-          cur[i >> 1] |= (i & 1) ? (v << 16) : v;
-        }
-        float* dst = dring + (rp & (FAST_RING - 1)) * 32 + lane;
-#pragma unroll
-        for (int i = 0; i < FAST_CHUNK; ++i) {
-          if (i < (int)nnew) {
-            const int x = s16_at(cur, i);
-            const int x16 = (i < FAST_DCL) ? s16_at(rawh, i) : s16_at(cur, i - FAST_DCL);
-            const int x15 = (i < FAST_DCL - 1) ? s16_at(rawh, i + 1) : s16_at(cur, i - (FAST_DCL - 1));
-            S1 += x - x16;
-            S2 += S1 - s1h[i & 15];
-            s1h[i & 15] = S1;
-            const int D = (x15 << 8) - S2;
-            dst[i * 32] = (float)D * 0.00390625f;
-          }
-        }
-        // The DC windows are final now.  Store them to the state words right here, rotated so that index 0 is the
-        // oldest sample again (static register indices, run-time addresses — no dynamically indexed register arrays):
-        // the last 16 samples are old-history entries i >= nnew and chunk samples nnew-16 <= i < nnew; the S1 of chunk
-        // sample j lives in s1h[j & 15].
-#pragma unroll
-        for (int i = 0; i < FAST_DCL; ++i) {
-          if (i >= (int)nnew) LANE_ST(st, L, L.dc_ff + ((uint32_t)i - nnew)) = __float_as_uint((float)s16_at(rawh, i));
-          LANE_ST(st, L, L.dc_fb + (((uint32_t)i - nnew) & 15u)) = __float_as_uint((float)s1h[i] * 0.0625f);
-        }
-#pragma unroll
-        for (int i = 0; i < FAST_CHUNK; ++i) {
-          if (i < (int)nnew && i + FAST_DCL >= (int)nnew)
-            LANE_ST(st, L, L.dc_ff + ((uint32_t)(i + FAST_DCL) - nnew)) = __float_as_uint((float)s16_at(cur, i));
-        }
+        feed.take_partial(cur, rp, nnew);
+        dc_chunk_partial(dc, cur, (int)nnew, [&](int i, float d) { dst[i * 32] = d; });
+        dc_store_after_partial(dc, cur, nnew, DcToState{st, L});
         dc_windows_stored = true;
         rp += nnew;
       }
@@ -371,78 +568,28 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
     }
 
     // ---------------- segment: AGC over this lane's samples up to its next TED instant (A2, A3) ----------------
-    // Every lane runs the warp's longest trip count.  The first `nmin` samples (warp minimum) need no predicate at all;
-    // in the short tail, samples beyond a lane's own segment use bandwidth 0 (g + t*0 == g exactly; the stale d they
-    // read is finite) and store nothing.  The d loads of a group are issued together so that their latency is paid
-    // once per group, not once per sample.  Ring addresses are explicit 32-bit shared addresses: byte offset
-    // o = ((pos + k) & 63) * 128 + lane * 4 relative to each ring.
     int nseg = 0;
     if (pos < len && pend == 0u) nseg = min(cfire - a.clock, (int)(rp - pos));
-    if (((a.tedcnt ^ round_ctr) & 1u) != 0u) nseg = 0;   // TED-phase alignment, see below
+    if (((a.tedcnt ^ round_ctr) & 1u) != 0u) nseg = 0;   // TED-phase alignment, see above
     const int maxseg = __reduce_max_sync(0xffffffffu, nseg);
     const int nmin = __reduce_min_sync(0xffffffffu, nseg);
     const float bw_eff = (a.flags & FLAG_AGC_LOCKED) ? 0.0f : bw;   // (!locked as f32) * (1-|y|) * bw   agc.rs:74
-    float g = a.g;
-    uint32_t o = ((pos << 7) & 0x1f80u) | ((uint32_t)lane << 2);
-    int k = 0;
-    for (; k + 4 <= nmin; k += 4) {
-      float dv[4]; uint32_t oo[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { oo[j] = o; dv[j] = lds_f32(d_base + o); o = (o + 128u) & 0x1fffu; }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float y = FMUL(dv[j], g);                                               // agc.rs:73
-        g = fminf(fmaxf(FADD(g, FMUL(FSUB(1.0f, fabsf(y)), bw_eff)), gmin), gmax);    // agc.rs:74-75
-        sts_f32_mirrored(y_base + oo[j], y);                                          // demod.rs:177-179
-      }
-    }
-    for (; k < maxseg; k += 2) {
-      float dv[2]; uint32_t oo[2];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) { oo[j] = o; dv[j] = lds_f32(d_base + o); o = (o + 128u) & 0x1fffu; }
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const bool act = (k + j) < nseg;
-        const float bwk = act ? bw_eff : 0.0f;
-        const float y = FMUL(dv[j], g);
-        g = fminf(fmaxf(FADD(g, FMUL(FSUB(1.0f, fabsf(y)), bwk)), gmin), gmax);
-        if (act) sts_f32_mirrored(y_base + oo[j], y);
-      }
-    }
-    a.g = g;
+    const uint32_t o = ((pos << 7) & 0x1f80u) | ((uint32_t)lane << 2);
+    a.g = agc_segment<0x1fffu, MIRROR>(a.g, bw_eff, gmin, gmax, d_base, y_base, o, o, 0, nmin, maxseg, nseg);
     pos += (uint32_t)nseg;
     a.clock += nseg;
     const bool fire = (nseg > 0) && (a.clock == cfire);
     bool have_sym = false;
     if (__any_sync(0xffffffffu, fire)) {
-
-    // ---------------- TED instant: matched filters (A4) with packed exact f32 ops ----------------
-    // fma(v, h, -0) == RN(v*h) and fma(acc, 1, prod) == RN(acc + prod): two separately rounded operations per tap
-    // and accumulator, as filter.rs:363-377 requires.  The -0 and 1 operands are run-time values (SameParams) so that
-    // ptxas cannot fold the pair back into one fused multiply-add.
-    float soft;
-    {
-      int nslot = (int)((pos - 1u) & (FAST_RING - 1));
-      if (nslot < FAST_NTAPS - 1) nslot += FAST_RING;
-      const float* yp = yring + nslot * 32 + lane;
-      float2 am = make_float2(0.0f, 0.0f), as = make_float2(0.0f, 0.0f);
-#pragma unroll
-      for (int i = 0; i < FAST_NTAPS; ++i) {
-        const float v = yp[-i * 32];
-        const float4 t = tapsm[i];
-        const float2 vv = make_float2(v, v);
-        am = __ffma2_rn(am, one2, __ffma2_rn(vv, make_float2(t.x, t.y), negz2));
-        as = __ffma2_rn(as, one2, __ffma2_rn(vv, make_float2(t.z, t.w), negz2));
+      // ---------------- TED instant: matched filters (A4), timing loop (A5) ----------------
+      const float soft = mf_soft<MIRROR>(yring, tapsm, lane, pos, one2, negz2);
+      if (fire) {
+        const float rem = FSUB(a.until, (float)a.clock);  // receiver.rs:352
+        a.clock = 0;
+        have_sym = ted_step(a, p, soft, rem);
+        cfire = fire_clock(a.until, 0);
       }
-      soft = rclamp(FSUB(hypot_fixed(am.x, am.y), hypot_fixed(as.x, as.y)), -1.0f, 1.0f);  // demod.rs:163
     }
-    if (fire) {
-      const float rem = FSUB(a.until, (float)a.clock);  // receiver.rs:352
-      a.clock = 0;
-      have_sym = ted_step(a, p, soft, rem);
-      cfire = fire_clock(a.until, 0);
-    }
-    }  // any(fire)
 
     // ---------------- symbol: squelch now (A6), byte path (A7-A9) on the aligned rounds ----------------
     if (have_sym) pend = symbol_squelch(a, p, s, st, blob, a.ted1, a.ted2, a.n0 + pos);
@@ -458,17 +605,76 @@ __global__ void __launch_bounds__(32) same_rx_fast_kernel(const __grid_constant_
 
   // ---- store state (same f32 layout as the generic kernel) ----
   lane_store(a, p, st, a.n0 + len);
-  LANE_ST(st, L, F_DC_FFSUM) = __float_as_uint((float)S1);
-  LANE_ST(st, L, F_DC_FBSUM) = __float_as_uint((float)S2 * 0.0625f);
-  if (!dc_windows_stored) {
-#pragma unroll
-    for (int i = 0; i < FAST_DCL; ++i) {
-      LANE_ST(st, L, L.dc_ff + i) = __float_as_uint((float)s16_at(rawh, i));
-      LANE_ST(st, L, L.dc_fb + i) = __float_as_uint((float)s1h[i] * 0.0625f);
-    }
+  if (TILE_FED) {
+    // commit the DC-blocker state the front-end kernel left for this stream (it could not write the state words
+    // itself: its first run of each stream was still reading them)
+    for (int w = 0; w < DCW_WORDS; ++w) DcToState{st, L}((uint32_t)w, tiles.dc_next[(size_t)w * L.n_pad + s]);
+  } else if (!dc_windows_stored) {
+    dc_store(dc, DcToState{st, L});
   }
   for (int i = 0; i < FAST_NTAPS; ++i)
     LANE_ST(st, L, L.win + i) = __float_as_uint(yring[((int)(len + i - FAST_NTAPS) & (FAST_RING - 1)) * 32 + lane]);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Front-end kernel (feed-forward stages A0 + A1, time-parallel): s16 stream-major -> exact DC-blocked f32 in lane-major
+// tiles  d[(tile * n_max + n) * 32 + lane],  tile = 32 consecutive streams — one 128-byte line per (tile, sample), the
+// layout a warp of the loop kernel reads with one coalesced request.  HBM-bound: 2 B read + 4 B written per sample.
+//
+// One warp = one tile x one run of FE_RUN samples; lane = stream.  The DC blocker has finite memory (31 samples), so a
+// run that does not start the chunk warms up on the 32 samples before it (integer recursion from zero is exact after
+// 31 samples) and is independent of every other run; the first run of a stream starts from the resident state.  Reads:
+// each lane streams along its own row with 16-byte loads (L1 keeps the 128-byte lines between a lane's consecutive
+// loads); writes: 32 lanes x 4 B = one full line per sample.  The run that ends a stream's chunk writes the new DC
+// state to tiles.dc_next (committed to the state words by the tile-fed loop kernel).
+// ----------------------------------------------------------------------------------------------------------------
+#define FE_RUN 512
+#define FE_WARPS 4
+__global__ void __launch_bounds__(FE_WARPS * 32) same_frontend_kernel(const __grid_constant__ SameParams p,
+                                                                      const int16_t* __restrict__ samples,
+                                                                      const unsigned long long* __restrict__ offsets,
+                                                                      const uint32_t* __restrict__ lengths,
+                                                                      const SameTiles tiles) {
+  const SameLayout& L = p.layout;
+  const int lane = threadIdx.x & 31;
+  const uint32_t tile = blockIdx.y;
+  const uint32_t run = blockIdx.x * FE_WARPS + (threadIdx.x >> 5);
+  const uint32_t s = tile * 32u + (uint32_t)lane;
+  const bool valid = s < p.n_streams;
+  const uint32_t len = valid ? lengths[s] : 0u;
+  const uint32_t r0 = run * FE_RUN;
+  if (r0 >= len) return;
+  const uint32_t r1 = min(r0 + (uint32_t)FE_RUN, len);
+  const int16_t* src = samples + offsets[s];
+  uint32_t* st = p.state32 + s;
+
+  DcInt dc;
+  RawFeed feed;
+  uint32_t cur[FAST_CHUNK / 2];
+  if (run == 0) {
+    dc_load(dc, st, L);
+    feed.init(src, 0u, len);
+  } else {
+    dc_zero(dc);
+    feed.init(src, r0 - FAST_CHUNK, len);
+    feed.take_full(cur, r0 - FAST_CHUNK, len);
+    dc_chunk(dc, cur, [](int, float) {});          // warm-up: exact from the 32nd sample on
+  }
+  float* dst = tiles.d + ((size_t)tile * tiles.n_max + r0) * 32u + (uint32_t)lane;
+  uint32_t c = r0;
+  for (; c + FAST_CHUNK <= r1; c += FAST_CHUNK, dst += FAST_CHUNK * 32) {
+    feed.take_full(cur, c, len);
+    dc_chunk(dc, cur, [&](int i, float d) { __stcs(dst + i * 32, d); });
+  }
+  const auto to_next = [&](uint32_t w, uint32_t bits) { tiles.dc_next[(size_t)w * L.n_pad + s] = bits; };
+  if (c < r1) {                                      // r1 == len: the partial tail of the chunk
+    const uint32_t nnew = r1 - c;
+    feed.take_partial(cur, c, nnew);
+    dc_chunk_partial(dc, cur, (int)nnew, [&](int i, float d) { __stcs(dst + i * 32, d); });
+    dc_store_after_partial(dc, cur, nnew, to_next);
+  } else if (r1 == len) {
+    dc_store(dc, to_next);
+  }
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -508,31 +714,12 @@ __device__ __forceinline__ void ws_producer(const SameParams& p, uint32_t* st, c
                                             volatile uint32_t* sh_pos, volatile uint32_t* sh_done, const int bar_pos,
                                             const int bar_pos_n, const int bar_data, const int bar_data_n) {
   const SameLayout& L = p.layout;
-  const bool src_aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
-  uint32_t rawh[FAST_DCL / 2];   // last 16 raw samples, packed pairs, oldest first   (ff window, dcblock.rs:63)
-  int s1h[FAST_DCL];             // S1 = 16 * ma0 for the last 16 samples            (fb window)
-  int S1 = __float2int_rn(__uint_as_float(LANE_ST(st, L, F_DC_FFSUM)));
-  int S2 = __float2int_rn(__uint_as_float(LANE_ST(st, L, F_DC_FBSUM)) * 16.0f);
-#pragma unroll
-  for (int i = 0; i < FAST_DCL / 2; ++i) {
-    int lo = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_ff + 2 * i)));
-    int hi = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_ff + 2 * i + 1)));
-    rawh[i] = ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16);
-  }
-#pragma unroll
-  for (int i = 0; i < FAST_DCL; ++i) s1h[i] = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_fb + i)) * 16.0f);
-
+  DcInt dc;
+  RawFeed feed;
+  dc_load(dc, st, L);
+  feed.init(src, 0u, len);
   uint32_t rp = 0;
   bool dc_windows_stored = false;
-  int4 nx[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) nx[i] = make_int4(0, 0, 0, 0);
-  bool pf_ok = src != nullptr && src_aligned && len >= (uint32_t)FAST_CHUNK;
-  if (pf_ok) {
-    const int4* q = reinterpret_cast<const int4*>(src);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) nx[i] = __ldg(q + i);
-  }
   bool first = true;
   while (true) {
     if (!first) {
@@ -544,74 +731,17 @@ __device__ __forceinline__ void ws_producer(const SameParams& p, uint32_t* st, c
     // every lane with room for a whole chunk takes one: afterwards it holds >= 32 samples, more than any segment
     const bool take = (rp < len) && (rp - cpos) <= (uint32_t)(WS_DRING - FAST_CHUNK);
     const uint32_t nnew = take ? min((uint32_t)FAST_CHUNK, len - rp) : 0u;
+    float* dst = dring + (rp & (WS_DRING - 1)) * 32 + lane;  // rp % 32 == 0: the chunk never wraps
     if (nnew == FAST_CHUNK) {
       uint32_t cur[FAST_CHUNK / 2];
-      if (pf_ok) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { cur[4 * i] = nx[i].x; cur[4 * i + 1] = nx[i].y; cur[4 * i + 2] = nx[i].z; cur[4 * i + 3] = nx[i].w; }
-      } else {
-#pragma unroll
-        for (int i = 0; i < FAST_CHUNK / 2; ++i) {
-          const uint32_t lo = src ? (uint32_t)(uint16_t)src[rp + 2 * i] : 0u;
-          const uint32_t hi = src ? (uint32_t)(uint16_t)src[rp + 2 * i + 1] : 0u;
-          cur[i] = lo | (hi << 16);
-        }
-      }
-      pf_ok = src != nullptr && src_aligned && (len - rp) >= 2u * FAST_CHUNK;
-      if (pf_ok) {
-        const int4* q = reinterpret_cast<const int4*>(src + rp + FAST_CHUNK);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) nx[i] = __ldg(q + i);
-      }
-      float* dst = dring + (rp & (WS_DRING - 1)) * 32 + lane;  // rp % 32 == 0: the chunk never wraps
-#pragma unroll
-      for (int i = 0; i < FAST_CHUNK; ++i) {
-        const int x = s16_at(cur, i);
-        const int x16 = (i < FAST_DCL) ? s16_at(rawh, i) : s16_at(cur, i - FAST_DCL);
-        const int x15 = (i < FAST_DCL - 1) ? s16_at(rawh, i + 1) : s16_at(cur, i - (FAST_DCL - 1));
-        S1 += x - x16;                    // ff: moving_sum += input - aged          dcblock.rs:106
-        S2 += S1 - s1h[i & 15];           // fb: moving_sum += ma0 - aged            dcblock.rs:106
-        s1h[i & 15] = S1;
-        const int D = (x15 << 8) - S2;    // 256 * (sig - ma1)                       dcblock.rs:48
-        dst[i * 32] = (float)D * 0.00390625f;
-      }
-#pragma unroll
-      for (int i = 0; i < FAST_DCL / 2; ++i) rawh[i] = cur[FAST_CHUNK / 2 - FAST_DCL / 2 + i];
+      feed.take_full(cur, rp, len);
+      dc_chunk(dc, cur, [&](int i, float d) { dst[i * 32] = d; });
       rp += FAST_CHUNK;
     } else if (nnew) {
       uint32_t cur[FAST_CHUNK / 2];
-#pragma unroll
-      for (int i = 0; i < FAST_CHUNK / 2; ++i) cur[i] = 0u;
-#pragma unroll
-      for (int i = 0; i < FAST_CHUNK; ++i) {
-        const uint32_t v = (src && i < (int)nnew) ? (uint32_t)(uint16_t)src[rp + i] : 0u;
-        cur[i >> 1] |= (i & 1) ? (v << 16) : v;
-      }
-      float* dst = dring + (rp & (WS_DRING - 1)) * 32 + lane;
-#pragma unroll
-      for (int i = 0; i < FAST_CHUNK; ++i) {
-        if (i < (int)nnew) {
-          const int x = s16_at(cur, i);
-          const int x16 = (i < FAST_DCL) ? s16_at(rawh, i) : s16_at(cur, i - FAST_DCL);
-          const int x15 = (i < FAST_DCL - 1) ? s16_at(rawh, i + 1) : s16_at(cur, i - (FAST_DCL - 1));
-          S1 += x - x16;
-          S2 += S1 - s1h[i & 15];
-          s1h[i & 15] = S1;
-          const int D = (x15 << 8) - S2;
-          dst[i * 32] = (float)D * 0.00390625f;
-        }
-      }
-      // final DC windows, rotated so that index 0 is the oldest sample again (see same_rx_fast_kernel)
-#pragma unroll
-      for (int i = 0; i < FAST_DCL; ++i) {
-        if (i >= (int)nnew) LANE_ST(st, L, L.dc_ff + ((uint32_t)i - nnew)) = __float_as_uint((float)s16_at(rawh, i));
-        LANE_ST(st, L, L.dc_fb + (((uint32_t)i - nnew) & 15u)) = __float_as_uint((float)s1h[i] * 0.0625f);
-      }
-#pragma unroll
-      for (int i = 0; i < FAST_CHUNK; ++i) {
-        if (i < (int)nnew && i + FAST_DCL >= (int)nnew)
-          LANE_ST(st, L, L.dc_ff + ((uint32_t)(i + FAST_DCL) - nnew)) = __float_as_uint((float)s16_at(cur, i));
-      }
+      feed.take_partial(cur, rp, nnew);
+      dc_chunk_partial(dc, cur, (int)nnew, [&](int i, float d) { dst[i * 32] = d; });
+      dc_store_after_partial(dc, cur, nnew, DcToState{st, L});   // final DC windows, back in canonical order
       dc_windows_stored = true;
       rp += nnew;
     }
@@ -619,17 +749,7 @@ __device__ __forceinline__ void ws_producer(const SameParams& p, uint32_t* st, c
     __threadfence_block();             // d values and rp visible before the consumer is released
     ws_bar_arrive(bar_data, bar_data_n);
   }
-  if (valid && len != 0u) {
-    LANE_ST(st, L, F_DC_FFSUM) = __float_as_uint((float)S1);
-    LANE_ST(st, L, F_DC_FBSUM) = __float_as_uint((float)S2 * 0.0625f);
-    if (!dc_windows_stored) {
-#pragma unroll
-      for (int i = 0; i < FAST_DCL; ++i) {
-        LANE_ST(st, L, L.dc_ff + i) = __float_as_uint((float)s16_at(rawh, i));
-        LANE_ST(st, L, L.dc_fb + i) = __float_as_uint((float)s1h[i] * 0.0625f);
-      }
-    }
-  }
+  if (valid && len != 0u && !dc_windows_stored) dc_store(dc, DcToState{st, L});
 }
 
 __global__ void __launch_bounds__(WS_THREADS) same_rx_ws_kernel(const __grid_constant__ SameParams p,
@@ -714,8 +834,7 @@ __global__ void __launch_bounds__(WS_THREADS) same_rx_ws_kernel(const __grid_con
         for (int j = 0; j < WS_SPEC; ++j) { dsp[j] = lds_f32(d_base + sd); sd = (sd + 128u) & 0x3fffu; }
 #pragma unroll
         for (int j = 0; j < WS_SPEC; ++j) {
-          const float y = FMUL(dsp[j], gs);                                                 // agc.rs:73
-          gs = fminf(fmaxf(FADD(gs, FMUL(FSUB(1.0f, fabsf(y)), bw_eff)), gmin), gmax);      // agc.rs:74-75
+          const float y = agc_step(gs, dsp[j], bw_eff, gmin, gmax);                         // agc.rs:72-77
           sts_f32_mirrored(y_base + sy, y);
           sts_f32(g_base + (uint32_t)(j * 128), gs);
           sy = (sy + 128u) & 0x1fffu;
@@ -761,39 +880,10 @@ __global__ void __launch_bounds__(WS_THREADS) same_rx_ws_kernel(const __grid_con
     const bool use_pre = __all_sync(0xffffffffu, nseg == 0 || pre_ok);
     float g = a.g;
     if (use_pre && nseg > 0) g = lds_f32(g_base + (uint32_t)((min(nseg, WS_SPEC) - 1) << 7));
-    int k = use_pre ? WS_SPEC : 0;
-    uint32_t od = (((pos + (uint32_t)k) << 7) & 0x3f80u) | ((uint32_t)lane << 2);   // d ring: 128 slots
-    uint32_t oy = (((pos + (uint32_t)k) << 7) & 0x1f80u) | ((uint32_t)lane << 2);   // y ring: 64 slots + mirror
-    for (; k + 4 <= nmin; k += 4) {
-      float dv[4]; uint32_t oo[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        oo[j] = oy; dv[j] = lds_f32(d_base + od);
-        od = (od + 128u) & 0x3fffu; oy = (oy + 128u) & 0x1fffu;
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float y = FMUL(dv[j], g);                                               // agc.rs:73
-        g = fminf(fmaxf(FADD(g, FMUL(FSUB(1.0f, fabsf(y)), bw_eff)), gmin), gmax);    // agc.rs:74-75
-        sts_f32_mirrored(y_base + oo[j], y);                                          // demod.rs:177-179
-      }
-    }
-    for (; k < maxseg; k += 2) {
-      float dv[2]; uint32_t oo[2];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        oo[j] = oy; dv[j] = lds_f32(d_base + od);
-        od = (od + 128u) & 0x3fffu; oy = (oy + 128u) & 0x1fffu;
-      }
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const bool act = (k + j) < nseg;
-        const float bwk = act ? bw_eff : 0.0f;
-        const float y = FMUL(dv[j], g);
-        g = fminf(fmaxf(FADD(g, FMUL(FSUB(1.0f, fabsf(y)), bwk)), gmin), gmax);
-        if (act) sts_f32_mirrored(y_base + oo[j], y);
-      }
-    }
+    const int k0 = use_pre ? WS_SPEC : 0;
+    const uint32_t od = (((pos + (uint32_t)k0) << 7) & 0x3f80u) | ((uint32_t)lane << 2);   // d ring: 128 slots
+    const uint32_t oy = (((pos + (uint32_t)k0) << 7) & 0x1f80u) | ((uint32_t)lane << 2);   // y ring: 64 slots + mirror
+    g = agc_segment<0x3fffu, true>(g, bw_eff, gmin, gmax, d_base, y_base, od, oy, k0, nmin, maxseg, nseg);
     if (nseg > 0) a.g = g;
     pre_ok = false;
     pos += (uint32_t)nseg;
@@ -809,23 +899,8 @@ __global__ void __launch_bounds__(WS_THREADS) same_rx_ws_kernel(const __grid_con
     ws_bar_arrive(WS_BAR_POS, WS_THREADS);
     bool have_sym = false;
     if (__any_sync(0xffffffffu, fire)) {
-      // ---------------- TED instant: matched filters (A4) with packed exact f32 ops (see same_rx_fast_kernel) ----------------
-      float soft;
-      {
-        int nslot = (int)((pos - 1u) & (FAST_RING - 1));
-        if (nslot < FAST_NTAPS - 1) nslot += FAST_RING;
-        const float* yp = yring + nslot * 32 + lane;
-        float2 am = make_float2(0.0f, 0.0f), as = make_float2(0.0f, 0.0f);
-#pragma unroll
-        for (int i = 0; i < FAST_NTAPS; ++i) {
-          const float v = yp[-i * 32];
-          const float4 t = tapsm[i];
-          const float2 vv = make_float2(v, v);
-          am = __ffma2_rn(am, one2, __ffma2_rn(vv, make_float2(t.x, t.y), negz2));
-          as = __ffma2_rn(as, one2, __ffma2_rn(vv, make_float2(t.z, t.w), negz2));
-        }
-        soft = rclamp(FSUB(hypot_fixed(am.x, am.y), hypot_fixed(as.x, as.y)), -1.0f, 1.0f);  // demod.rs:163
-      }
+      // ---------------- TED instant: matched filters (A4, packed exact f32 ops), timing loop (A5) ----------------
+      const float soft = mf_soft<true>(yring, tapsm, lane, pos, one2, negz2);
       if (fire) {
         const float rem = FSUB(a.until, (float)a.clock);  // receiver.rs:352
         a.clock = 0;
@@ -899,7 +974,8 @@ __device__ __forceinline__ float pk_mag(const float* yring, const float2* __rest
   return hypot_fixed(re, im);
 }
 
-__global__ void __launch_bounds__(PK_THREADS) same_rx_pipe_kernel(const __grid_constant__ SameParams p,
+// one block per SM at most (engine policy): every register the role code wants
+__global__ void __launch_bounds__(PK_THREADS, 1) same_rx_pipe_kernel(const __grid_constant__ SameParams p,
                                                                   const __grid_constant__ SameTaps2 taps,
                                                                   const int16_t* __restrict__ samples,
                                                                   const unsigned long long* __restrict__ offsets,
@@ -992,8 +1068,7 @@ __global__ void __launch_bounds__(PK_THREADS) same_rx_pipe_kernel(const __grid_c
         for (int j = 0; j < 8; ++j) {
           const uint32_t o2 = (o1 + 128u) & 0x3f80u;
           const float d2 = lds_f32(d_lane + o2);
-          const float y = FMUL(d0, g);                                                    // agc.rs:73
-          g = fminf(fmaxf(FADD(g, FMUL(FSUB(1.0f, fabsf(y)), bw_eff)), gmin), gmax);      // agc.rs:74-75
+          const float y = agc_step(g, d0, bw_eff, gmin, gmax);                            // agc.rs:72-77
           asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.f32 [%0+16384], %2;\n\tst.shared.f32 [%0+32768], %2;"
                        ::"r"(g_lane + o0), "f"(g), "f"(y) : "memory");                     // gain | y | y mirror
           o0 = o1; o1 = o2; d0 = d1; d1 = d2;
@@ -1059,8 +1134,8 @@ __global__ void __launch_bounds__(PK_THREADS) same_rx_pipe_kernel(const __grid_c
       for (int k = 0; k < nfb; ++k) {
         const bool act = need_fb && k < nseg;
         const float dv = lds_f32(d_lane + (((pos + (uint32_t)k) & (WS_DRING - 1)) << 7));
-        const float y = FMUL(dv, g);
-        const float gn = fminf(fmaxf(FADD(g, FMUL(FSUB(1.0f, fabsf(y)), bw_eff)), gmin), gmax);
+        float gn = g;
+        const float y = agc_step(gn, dv, bw_eff, gmin, gmax);
         if (act) {
           g = gn;
           const uint32_t slot = (pos + (uint32_t)k) & (PK_YRING - 1);
@@ -1194,20 +1269,34 @@ __global__ void same_evsort_scatter(const same_event* __restrict__ ev, uint32_t 
 // ----------------------------------------------------------------------------------------------------------------
 // Launchers (called from same_engine.cu)
 // ----------------------------------------------------------------------------------------------------------------
+// kernel ids: 1 generic, 2 single-warp fast, 3 pipelined four-warp, 4 three-warp, 5 single-warp fast fed by the front-end
+// kernel's tiles (split pipeline).  `fast_variant`: 0 = y ring with mirror slots, 1 = without (more resident warps).
 extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps, const SameTaps2* taps2, int force_generic,
                                       uint32_t lanes_per_warp, const void* d_samples_v, int sample_fmt,
                                       const unsigned long long* d_offsets, const uint32_t* d_lengths,
-                                      cudaStream_t stream) {
+                                      const SameTiles* tiles, int fast_variant, cudaStream_t stream) {
   const uint32_t blocks = (p->n_streams + 31u) / 32u;
   const int16_t* d_samples = static_cast<const int16_t*>(d_samples_v);
-  // force_generic: 1 = generic kernel, 2 = single-warp fast kernel, 3 = pipelined four-warp kernel,
-  //                4 (or 0) = three-warp kernel.  The fast kernels need the 22050 Hz geometry (42 taps, DC length 16)
-  //                and s16 samples (their DC blocker is an integer recursion).
+  // The fast kernels need the 22050 Hz geometry (42 taps, DC length 16) and s16 samples (their DC blocker is an
+  // integer recursion).
   if (sample_fmt == 0 && force_generic != 1 && p->ntaps == FAST_NTAPS && p->dc_len == FAST_DCL) {
-    const uint32_t lanes = lanes_per_warp ? lanes_per_warp : 32u;
+    const uint32_t lanes = (force_generic == 5) ? 32u : (lanes_per_warp ? lanes_per_warp : 32u);
     const uint32_t fblocks = (p->n_streams + lanes - 1u) / lanes;
-    if (force_generic == 2) {
-      same_dev::same_rx_fast_kernel<<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes);
+    SameTiles t{nullptr, nullptr, 0u};
+    if (force_generic == 5) {
+      if (!tiles || !tiles->d || !d_samples) return cudaErrorInvalidValue;
+      t = *tiles;
+      const dim3 grid((t.n_max + FE_RUN * FE_WARPS - 1u) / (FE_RUN * FE_WARPS), blocks);
+      same_dev::same_frontend_kernel<<<grid, FE_WARPS * 32, 0, stream>>>(*p, d_samples, d_offsets, d_lengths, t);
+      if (fast_variant == 1)
+        same_dev::same_rx_fast_kernel<true, false, 12><<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes, t);
+      else
+        same_dev::same_rx_fast_kernel<true, true, 1><<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes, t);
+    } else if (force_generic == 2) {
+      if (fast_variant == 1)
+        same_dev::same_rx_fast_kernel<false, false, 12><<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes, t);
+      else
+        same_dev::same_rx_fast_kernel<false, true, 1><<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes, t);
     } else if (force_generic == 3) {
       // per device, cheap: set on every launch rather than tracking which devices have seen it
       cudaError_t e = cudaFuncSetAttribute(same_dev::same_rx_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1230,6 +1319,15 @@ extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps,
       else same_dev::same_rx_generic_kernel<128, 64, int16_t><<<blocks, 32, smem, stream>>>(*p, *taps, d_samples, d_offsets, d_lengths);
     }
   }
+  return cudaGetLastError();
+}
+
+// The front-end kernel alone (measurement of the HBM-bound feed-forward stage; the resident state is not touched).
+extern "C" cudaError_t same_launch_frontend(const SameParams* p, const int16_t* d_samples, const unsigned long long* d_offsets,
+                                            const uint32_t* d_lengths, const SameTiles* tiles, cudaStream_t stream) {
+  const uint32_t blocks = (p->n_streams + 31u) / 32u;
+  const dim3 grid((tiles->n_max + FE_RUN * FE_WARPS - 1u) / (FE_RUN * FE_WARPS), blocks);
+  same_dev::same_frontend_kernel<<<grid, FE_WARPS * 32, 0, stream>>>(*p, d_samples, d_offsets, d_lengths, *tiles);
   return cudaGetLastError();
 }
 

@@ -135,6 +135,15 @@ struct SameParams {
   float f_one, f_negzero;
 };
 
+// Output of the front-end kernel (same_frontend_kernel), input of the tile-fed loop kernel: exact DC-blocked f32 samples
+// in lane-major tiles, sample n of stream s at d[((s / 32) * n_max + n) * 32 + (s % 32)], plus the DC-blocker state the
+// front end leaves behind (34 words per stream, word-major like state32).
+struct SameTiles {
+  float* d;
+  uint32_t* dc_next;
+  uint32_t n_max;      // samples per stream in the tile buffer (multiple of 32)
+};
+
 struct SameTaps2 {                // the same taps as (re, im) pairs for the packed-FFMA2 matched filter
   float2 mark[64], space[64];
 };

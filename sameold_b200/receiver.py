@@ -531,6 +531,15 @@ class SameBatchReceiver:
     def set_option(self, key: str, value: int):
         self._ck(self._lib.same_engine_set_option(self._h, key.encode(), int(value)))
 
+    def frontend_probe(self, d_ptr: int, total_samples: int, offsets: np.ndarray, lengths: np.ndarray, reps: int = 5) -> float:
+        """ms per launch of the front-end kernel alone on device-resident samples (measurement aid)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        lengths = np.ascontiguousarray(lengths, dtype=np.uint32)
+        ms = C.c_float()
+        self._ck(self._lib.same_engine_frontend_probe(self._h, C.c_void_p(d_ptr), int(total_samples), offsets.ctypes.data,
+                                                      lengths.ctypes.data, int(reps), C.byref(ms)))
+        return ms.value
+
     def get_option(self, key: str) -> int:
         v = C.c_int()
         self._ck(self._lib.same_engine_get_option(self._h, key.encode(), C.byref(v)))

@@ -237,7 +237,8 @@ def test_fast_and_generic_kernels_agree():
     got = [[] for _ in recs]
     k = 0
     while any(p < len(r) for p, r in zip(pos, recs)):
-        rx.set_option("kernel", 1 + k % 4)   # 1 generic, 2 single-warp fast, 3 pipelined, 4 three-warp
+        rx.set_option("kernel", 1 + k % 5)   # 1 generic, 2 single-warp fast, 3 pipelined, 4 three-warp, 5 split (front end + tile-fed)
+        rx.set_option("fast_variant", (k // 5) % 2)   # single-warp kernel's window ring with / without mirror slots
         k += 1
         chunks = []
         for s_ in range(len(recs)):
@@ -253,7 +254,7 @@ def test_fast_and_generic_kernels_agree():
         assert_events_equal(want[s_], o.events(), f"stream {s_} generic kernel vs oracle")
 
 
-@pytest.mark.parametrize("kernel", [2, 3, 4])
+@pytest.mark.parametrize("kernel", [2, 3, 4, 5, 12, 15])
 def test_each_fast_kernel_matches_oracle(kernel):
     """Every fast-kernel flavour on its own, whole streams in one submit and in 3 s chunks: golden recordings and
     synthetic streams with bursts against the oracle, event for event."""
@@ -267,12 +268,14 @@ def test_each_fast_kernel_matches_oracle(kernel):
         o.process_s16(r)
         want.append(o.events())
     rx = b.build_batch(len(recs))
-    rx.set_option("kernel", kernel)
+    rx.set_option("kernel", kernel % 10)          # 1x = the same kernel with fast_variant 1 (no mirror slots)
+    rx.set_option("fast_variant", kernel // 10)
     got = rx.process(recs)
     for s_ in range(len(recs)):
         assert_events_equal(got[s_], want[s_], f"kernel {kernel} stream {s_} one submit")
     rx = b.build_batch(len(recs))
-    rx.set_option("kernel", kernel)
+    rx.set_option("kernel", kernel % 10)
+    rx.set_option("fast_variant", kernel // 10)
     got = [[] for _ in recs]
     step = 3 * 22050 + 7
     for lo in range(0, max(len(r) for r in recs), step):
@@ -352,8 +355,9 @@ def _rebase_seq(evs):
 def test_config3_full_size_every_stream_vs_oracle():
     """BASELINE config 3 at full size (4096 streams x 60 s, 10.8 GB of samples), BASELINE.md §3 row 3: the engine's
     events on EVERY stream are bit-identical to the CPU oracle's (kind, sample counter, symbol count, bytes, parity /
-    voting counts); the engine's kernel for this batch size (pipelined) run three times, and every other kernel once,
-    produce the same event stream; every stream decodes its planned header."""
+    voting counts); the engine's kernel for this batch size (pipelined) run three times, and every other kernel once
+    (generic, single-warp with and without mirror slots, three-warp, split front end + tile-fed), produce the same
+    event stream; every stream decodes its planned header."""
     _torch()
     ns, secs = 4096, 60.0
     buf, plans, n, stride = _device_corpus(ns, secs)
@@ -366,9 +370,10 @@ def test_config3_full_size_every_stream_vs_oracle():
     want = _canonical_raw(oe, op)
     del host
     ref = None
-    for kernel in (0, 0, 0, 1, 2, 4):
+    for kernel in (0, 0, 0, 1, 2, 4, 5, 12):
         rx = b.build_batch(ns)
-        rx.set_option("kernel", kernel)
+        rx.set_option("kernel", kernel % 10)
+        rx.set_option("fast_variant", kernel // 10)
         rx.submit_device(buf.data_ptr(), ns * stride, offsets, lengths)
         rx.sync()
         evs, pay = _canonical_raw(*rx.drain_raw())
@@ -399,8 +404,9 @@ def test_config4_65536_streams_time_chunked_two_shards_vs_oracle():
     torch = _torch()
     ns, secs, chunk_s, every = 65536, 60.0, 10.0, 64
     rate = 22050
-    n, cn = int(secs * rate), int(chunk_s * rate)
-    assert cn % 8 == 0 and n % cn == 0
+    n = int(secs * rate)
+    cn = (int(chunk_s * rate) + 7) // 8 * 8          # chunk starts must be multiples of 8 samples (generator window)
+    nchunks = (n + cn - 1) // cn
     plans = synth.plan_corpus(ns, rate, secs)
     corpus = synth.DeviceCorpus(plans, rate)
     buf = torch.empty((ns, cn), dtype=torch.int16, device="cuda")
@@ -409,13 +415,14 @@ def test_config4_65536_streams_time_chunked_two_shards_vs_oracle():
     assert [(f, c) for _, f, c in rx.shards()] == [(0, 32768), (32768, 32768)]
     host = torch.empty((ns // every, n), dtype=torch.int16, pin_memory=False)
     offsets = np.arange(ns, dtype=np.uint64) * np.uint64(cn)
-    lengths = np.full(ns, cn, np.uint32)
     import ctypes as C
     lib = rx._lib
     evs_all, pay_all, pay_base = [], [], 0
-    for c in range(n // cn):
-        corpus.generate(buf.data_ptr(), cn, cn, first_sample=c * cn)
-        host[:, c * cn:(c + 1) * cn] = buf[::every].cpu()
+    for c in range(nchunks):
+        w = min(cn, n - c * cn)                      # the last chunk is shorter
+        lengths = np.full(ns, w, np.uint32)
+        corpus.generate(buf.data_ptr(), cn, w, first_sample=c * cn)
+        host[:, c * cn:c * cn + w] = buf[::every, :w].cpu()
         for i, (_dev, first, count) in enumerate(rx.shards()):   # device-resident chunk: each shard's engine takes its rows
             eng = C.c_void_p(lib.same_multi_engine(rx._h, i))
             rc = lib.same_engine_submit_s16_device(eng, C.c_void_p(buf.data_ptr() + first * cn * 2), count * cn,
