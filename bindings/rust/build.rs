@@ -18,6 +18,7 @@ fn main() {
         .arg(&lib)
         .arg(csrc.join("same_kernels.cu"))
         .arg(csrc.join("same_engine.cu"))
+        .arg(csrc.join("same_multi.cu"))
         .status()
         .expect("nvcc not found: the B200 engine has no CPU fallback");
     assert!(status.success(), "nvcc failed");

@@ -9,8 +9,10 @@ use crate::ffi::*;
 use crate::{LinkState, Message, MessageDecodeErr, MessageHeader, SameReceiverBuilder, TransportState};
 use std::ptr;
 
+/// `n_streams` receivers sharded over one or more CUDA devices of this box: one engine + one host thread per device
+/// inside the native library (`same_multi_*`), no collective — streams are independent.
 pub struct SameBatchReceiver {
-    engine: *mut same_engine,
+    multi: *mut same_multi,
     n_streams: u32,
 }
 
@@ -24,6 +26,11 @@ pub struct BatchedEvent {
 impl SameBatchReceiver {
     /// == `SameReceiverBuilder::build()` for `n_streams` receivers on CUDA device `device`.
     pub fn new(builder: &SameReceiverBuilder, n_streams: u32, device: i32) -> Result<Self, String> {
+        Self::new_multi(builder, n_streams, &[device])
+    }
+
+    /// The same over several devices: stream i lives on `devices[i * devices.len() / n_streams]` (contiguous shards).
+    pub fn new_multi(builder: &SameReceiverBuilder, n_streams: u32, devices: &[i32]) -> Result<Self, String> {
         let (unlocked, locked) = builder.timing_bandwidth();
         let (open, close) = builder.squelch_power();
         let eq = builder.adaptive_equalizer();
@@ -48,13 +55,13 @@ impl SameBatchReceiver {
             frame_prefix_max_errors: builder.frame_prefix_max_errors(),
             frame_max_invalid_bytes: builder.frame_max_invalid(),
         };
-        let mut engine = ptr::null_mut();
-        let rc = unsafe { same_engine_create(&cfg, device, n_streams, &mut engine) };
+        let mut multi = ptr::null_mut();
+        let rc = unsafe { same_multi_create(&cfg, devices.as_ptr(), devices.len() as u32, n_streams, &mut multi) };
         if rc != 0 {
-            let msg = unsafe { std::ffi::CStr::from_ptr(same_last_error()) };
-            return Err(format!("same_engine_create: {} ({})", rc, msg.to_string_lossy()));
+            let msg = unsafe { std::ffi::CStr::from_ptr(same_multi_last_error(ptr::null())) };
+            return Err(format!("same_multi_create: {} ({})", rc, msg.to_string_lossy()));
         }
-        Ok(Self { engine, n_streams })
+        Ok(Self { multi, n_streams })
     }
 
     /// == `iter_events(chunk)` driven to exhaustion on every stream.  `chunks[i]` is stream i's next s16 samples
@@ -69,8 +76,25 @@ impl SameBatchReceiver {
             flat.extend_from_slice(c);
         }
         unsafe {
-            check(self.engine, same_engine_submit_s16(self.engine, flat.as_ptr(), flat.len() as u64, offsets.as_ptr(), lengths.as_ptr()))?;
-            check(self.engine, same_engine_sync(self.engine))?;
+            check(self.multi, same_multi_submit_s16(self.multi, flat.as_ptr(), flat.len() as u64, offsets.as_ptr(), lengths.as_ptr()))?;
+            check(self.multi, same_multi_sync(self.multi))?;
+        }
+        self.drain()
+    }
+
+    /// The reference's own item type: `iter_events<I: IntoIterator<Item = f32>>` (receiver.rs:119-130), any scale.
+    pub fn process_f32(&mut self, chunks: &[&[f32]]) -> Result<Vec<BatchedEvent>, String> {
+        assert_eq!(chunks.len(), self.n_streams as usize);
+        let mut flat = Vec::with_capacity(chunks.iter().map(|c| c.len()).sum());
+        let (mut offsets, mut lengths) = (Vec::new(), Vec::new());
+        for c in chunks {
+            offsets.push(flat.len() as u64);
+            lengths.push(c.len() as u32);
+            flat.extend_from_slice(c);
+        }
+        unsafe {
+            check(self.multi, same_multi_submit_f32(self.multi, flat.as_ptr(), flat.len() as u64, offsets.as_ptr(), lengths.as_ptr()))?;
+            check(self.multi, same_multi_sync(self.multi))?;
         }
         self.drain()
     }
@@ -89,11 +113,11 @@ impl SameBatchReceiver {
 
     fn drain(&mut self) -> Result<Vec<BatchedEvent>, String> {
         let (mut nev, mut npay) = (0usize, 0usize);
-        unsafe { check(self.engine, same_engine_pending(self.engine, &mut nev, &mut npay))? };
+        unsafe { check(self.multi, same_multi_pending(self.multi, &mut nev, &mut npay))? };
         let mut evs = vec![same_event::default(); nev];
         let mut pay = vec![0u8; npay.max(1)];
         unsafe {
-            check(self.engine, same_engine_drain_events(self.engine, evs.as_mut_ptr(), nev, &mut nev, pay.as_mut_ptr(), pay.len(), &mut npay))?;
+            check(self.multi, same_multi_drain_events(self.multi, evs.as_mut_ptr(), nev, &mut nev, pay.as_mut_ptr(), pay.len(), &mut npay))?;
         }
         Ok(evs
             .iter()
@@ -134,14 +158,14 @@ impl SameBatchReceiver {
 
 impl Drop for SameBatchReceiver {
     fn drop(&mut self) {
-        unsafe { same_engine_destroy(self.engine) }
+        unsafe { same_multi_destroy(self.multi) }
     }
 }
 
-unsafe fn check(e: *mut same_engine, rc: i32) -> Result<(), String> {
+unsafe fn check(m: *mut same_multi, rc: i32) -> Result<(), String> {
     if rc == 0 {
         Ok(())
     } else {
-        Err(format!("same_engine error {}: {}", rc, std::ffi::CStr::from_ptr(same_engine_last_error(e)).to_string_lossy()))
+        Err(format!("same_engine error {}: {}", rc, std::ffi::CStr::from_ptr(same_multi_last_error(m)).to_string_lossy()))
     }
 }

@@ -810,7 +810,7 @@ int same_engine_set_option(same_engine* e, const char* key, int value) {
   int rc = same_engine_sync(e);
   if (rc) return rc;
   if (strcmp(key, "kernel") == 0 || strcmp(key, "force_generic") == 0) {
-    if (value < 0 || value > 5) return fail(e, SAME_ERR_INVALID_ARG, "kernel must be 0 (policy), 1 generic, 2 single-warp, 3 pipelined, 4 three-warp or 5 split (front end + tile-fed)");
+    if (value < 0 || value > 6) return fail(e, SAME_ERR_INVALID_ARG, "kernel must be 0 (policy), 1 generic, 2 single-warp, 3 pipelined, 4 three-warp, 5 split (front end + tile-fed) or 6 dense single-warp");
     e->force_generic = value;
     return SAME_OK;
   }

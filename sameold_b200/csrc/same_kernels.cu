@@ -244,11 +244,12 @@ __device__ __forceinline__ void dc_zero(DcInt& q) {
   for (int i = 0; i < FAST_DCL; ++i) q.s1h[i] = 0;
 }
 
-// One full chunk of 32 samples (packed pairs in cur); emit(i, d) receives the DC-blocked sample i as exact f32.
-template <class Emit>
-__device__ __forceinline__ void dc_chunk(DcInt& q, const uint32_t (&cur)[FAST_CHUNK / 2], Emit&& emit) {
+// One full chunk of CHUNK (16 or 32) samples (packed pairs in cur); emit(i, d) receives the DC-blocked sample i as exact f32.
+template <int CHUNK, class Emit>
+__device__ __forceinline__ void dc_chunk(DcInt& q, const uint32_t (&cur)[CHUNK / 2], Emit&& emit) {
+  static_assert(CHUNK == 16 || CHUNK == 32, "the S1 history recycles in place: chunk = 1 or 2 DC lengths");
 #pragma unroll
-  for (int i = 0; i < FAST_CHUNK; ++i) {
+  for (int i = 0; i < CHUNK; ++i) {
     const int x = s16_at(cur, i);
     const int x16 = (i < FAST_DCL) ? s16_at(q.rawh, i) : s16_at(cur, i - FAST_DCL);
     const int x15 = (i < FAST_DCL - 1) ? s16_at(q.rawh, i + 1) : s16_at(cur, i - (FAST_DCL - 1));
@@ -259,15 +260,15 @@ __device__ __forceinline__ void dc_chunk(DcInt& q, const uint32_t (&cur)[FAST_CH
     emit(i, (float)D * 0.00390625f);
   }
 #pragma unroll
-  for (int i = 0; i < FAST_DCL / 2; ++i) q.rawh[i] = cur[FAST_CHUNK / 2 - FAST_DCL / 2 + i];
+  for (int i = 0; i < FAST_DCL / 2; ++i) q.rawh[i] = cur[CHUNK / 2 - FAST_DCL / 2 + i];
 }
 
-// The final, partial chunk of a submit (nnew < 32 samples; cur zero-filled beyond nnew).  The histories are NOT
+// The final, partial chunk of a submit (nnew < CHUNK samples; cur zero-filled beyond nnew).  The histories are NOT
 // rotated afterwards: dc_store_after_partial writes them out in canonical order.
-template <class Emit>
-__device__ __forceinline__ void dc_chunk_partial(DcInt& q, const uint32_t (&cur)[FAST_CHUNK / 2], const int nnew, Emit&& emit) {
+template <int CHUNK, class Emit>
+__device__ __forceinline__ void dc_chunk_partial(DcInt& q, const uint32_t (&cur)[CHUNK / 2], const int nnew, Emit&& emit) {
 #pragma unroll
-  for (int i = 0; i < FAST_CHUNK; ++i) {
+  for (int i = 0; i < CHUNK; ++i) {
     if (i < nnew) {
       const int x = s16_at(cur, i);
       const int x16 = (i < FAST_DCL) ? s16_at(q.rawh, i) : s16_at(cur, i - FAST_DCL);
@@ -296,8 +297,8 @@ __device__ __forceinline__ void dc_store(const DcInt& q, Store&& store) {
 // After a partial chunk of nnew samples: rotate so that index 0 is the oldest sample again (static register indices,
 // run-time word numbers -- no dynamically indexed register arrays).  The last 16 samples are old-history entries
 // i >= nnew and chunk samples nnew-16 <= i < nnew; the S1 of chunk sample j lives in s1h[j & 15].
-template <class Store>
-__device__ __forceinline__ void dc_store_after_partial(const DcInt& q, const uint32_t (&cur)[FAST_CHUNK / 2], const uint32_t nnew,
+template <int CHUNK, class Store>
+__device__ __forceinline__ void dc_store_after_partial(const DcInt& q, const uint32_t (&cur)[CHUNK / 2], const uint32_t nnew,
                                                        Store&& store) {
   store(DCW_FFSUM, __float_as_uint((float)q.S1));
   store(DCW_FBSUM, __float_as_uint((float)q.S2 * 0.0625f));
@@ -307,7 +308,7 @@ __device__ __forceinline__ void dc_store_after_partial(const DcInt& q, const uin
     store(DCW_FB + (((uint32_t)i - nnew) & 15u), __float_as_uint((float)q.s1h[i] * 0.0625f));
   }
 #pragma unroll
-  for (int i = 0; i < FAST_CHUNK; ++i) {
+  for (int i = 0; i < CHUNK; ++i) {
     if (i < (int)nnew && i + FAST_DCL >= (int)nnew)
       store(DCW_FF + ((uint32_t)(i + FAST_DCL) - nnew), __float_as_uint((float)s16_at(cur, i)));
   }
@@ -321,55 +322,58 @@ struct DcToState {
   }
 };
 
-// Raw-sample feed of one lane: 32-sample chunks as packed pairs, four 16-byte loads per chunk issued one chunk
-// ahead (a refill happens at most once per round, so the global-load latency overlaps a round of sequential work).
-struct RawFeed {
+// Raw-sample feed of one lane: CHUNK-sample chunks as packed pairs, 16-byte loads issued one chunk ahead (a refill
+// happens at most once or twice per round, so the global-load latency overlaps a round of sequential work).
+template <int CHUNK>
+struct RawFeedT {
+  static constexpr int NV = CHUNK / 8;   // int4 loads per chunk
   const int16_t* src;
-  int4 nx[4];
+  int4 nx[NV];
   bool aligned, pf_ok;
   __device__ __forceinline__ void init(const int16_t* s, uint32_t first, uint32_t len) {
     src = s;
     aligned = (reinterpret_cast<uintptr_t>(s) & 15u) == 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) nx[i] = make_int4(0, 0, 0, 0);
-    pf_ok = src != nullptr && aligned && first + (uint32_t)FAST_CHUNK <= len;
+    for (int i = 0; i < NV; ++i) nx[i] = make_int4(0, 0, 0, 0);
+    pf_ok = src != nullptr && aligned && first + (uint32_t)CHUNK <= len;
     if (pf_ok) {
       const int4* q = reinterpret_cast<const int4*>(src + first);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) nx[i] = __ldg(q + i);
+      for (int i = 0; i < NV; ++i) nx[i] = __ldg(q + i);
     }
   }
   // the full chunk at rp (rp % 8 == 0 relative to an aligned src); prefetches the chunk after it
-  __device__ __forceinline__ void take_full(uint32_t (&cur)[FAST_CHUNK / 2], uint32_t rp, uint32_t len) {
+  __device__ __forceinline__ void take_full(uint32_t (&cur)[CHUNK / 2], uint32_t rp, uint32_t len) {
     if (pf_ok) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { cur[4 * i] = nx[i].x; cur[4 * i + 1] = nx[i].y; cur[4 * i + 2] = nx[i].z; cur[4 * i + 3] = nx[i].w; }
+      for (int i = 0; i < NV; ++i) { cur[4 * i] = nx[i].x; cur[4 * i + 1] = nx[i].y; cur[4 * i + 2] = nx[i].z; cur[4 * i + 3] = nx[i].w; }
     } else {
 #pragma unroll
-      for (int i = 0; i < FAST_CHUNK / 2; ++i) {
+      for (int i = 0; i < CHUNK / 2; ++i) {
         const uint32_t lo = src ? (uint32_t)(uint16_t)src[rp + 2 * i] : 0u;
         const uint32_t hi = src ? (uint32_t)(uint16_t)src[rp + 2 * i + 1] : 0u;
         cur[i] = lo | (hi << 16);
       }
     }
-    pf_ok = src != nullptr && aligned && (len - rp) >= 2u * FAST_CHUNK;
+    pf_ok = src != nullptr && aligned && (len - rp) >= 2u * CHUNK;
     if (pf_ok) {
-      const int4* q = reinterpret_cast<const int4*>(src + rp + FAST_CHUNK);
+      const int4* q = reinterpret_cast<const int4*>(src + rp + CHUNK);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) nx[i] = __ldg(q + i);
+      for (int i = 0; i < NV; ++i) nx[i] = __ldg(q + i);
     }
   }
-  // a partial chunk of nnew < 32 samples at rp: scalar loads, zero-filled
-  __device__ __forceinline__ void take_partial(uint32_t (&cur)[FAST_CHUNK / 2], uint32_t rp, uint32_t nnew) const {
+  // a partial chunk of nnew < CHUNK samples at rp: scalar loads, zero-filled
+  __device__ __forceinline__ void take_partial(uint32_t (&cur)[CHUNK / 2], uint32_t rp, uint32_t nnew) const {
 #pragma unroll
-    for (int i = 0; i < FAST_CHUNK / 2; ++i) cur[i] = 0u;
+    for (int i = 0; i < CHUNK / 2; ++i) cur[i] = 0u;
 #pragma unroll
-    for (int i = 0; i < FAST_CHUNK; ++i) {
+    for (int i = 0; i < CHUNK; ++i) {
       const uint32_t v = (src && i < (int)nnew) ? (uint32_t)(uint16_t)src[rp + i] : 0u;
       cur[i >> 1] |= (i & 1) ? (v << 16) : v;
     }
   }
 };
+using RawFeed = RawFeedT<FAST_CHUNK>;
 
 // One AGC step (agc.rs:72-77): y = x*g; g += (!locked as f32)*(1-|y|)*bw; g = clamp(g, min, max).  `bw_eff` is bw or 0.
 __device__ __forceinline__ float agc_step(float& g, const float d, const float bw_eff, const float gmin, const float gmax) {
@@ -552,15 +556,15 @@ __global__ void __launch_bounds__(32, MIN_BLOCKS) same_rx_fast_kernel(const __gr
         // ---- full chunk: everything static, no per-sample predicates ----
         uint32_t cur[FAST_CHUNK / 2];
         feed.take_full(cur, rp, len);
-        dc_chunk(dc, cur, [&](int i, float d) { dst[i * 32] = d; });
+        dc_chunk<FAST_CHUNK>(dc, cur, [&](int i, float d) { dst[i * 32] = d; });
         rp += FAST_CHUNK;
       } else if (nnew) {
         // ---- final partial chunk of this submit (rp reaches len): scalar loads, per-sample predicates; the DC
         // windows are final now and are stored right here, rotated back into canonical order ----
         uint32_t cur[FAST_CHUNK / 2];
         feed.take_partial(cur, rp, nnew);
-        dc_chunk_partial(dc, cur, (int)nnew, [&](int i, float d) { dst[i * 32] = d; });
-        dc_store_after_partial(dc, cur, nnew, DcToState{st, L});
+        dc_chunk_partial<FAST_CHUNK>(dc, cur, (int)nnew, [&](int i, float d) { dst[i * 32] = d; });
+        dc_store_after_partial<FAST_CHUNK>(dc, cur, nnew, DcToState{st, L});
         dc_windows_stored = true;
         rp += nnew;
       }
@@ -617,6 +621,180 @@ __global__ void __launch_bounds__(32, MIN_BLOCKS) same_rx_fast_kernel(const __gr
 }
 
 // ----------------------------------------------------------------------------------------------------------------
+// Dense kernel: the single-warp fast kernel re-budgeted for RESIDENCY.  In the throughput regime every block lives for
+// the whole submit and a warp on its own issues only ~0.3 instructions per cycle (dependent AGC / accumulator chains),
+// so what matters is how many warps share a scheduler and that ALL blocks of the grid are resident at once: 65 536
+// streams are 2048 warps = 13.8 per SM, which at the fast kernel's 8 blocks per SM run as one wave of 8 and a tail wave
+// of 6 (measured: 0.49 issue slots used; profiles/ncu_r02_*).  This kernel fits DN_BLOCKS = 14 blocks per SM:
+//   * y ring without mirror slots (8 KB instead of 16): the matched filter wraps every tap address into the ring
+//     (2 integer ops per tap) instead of storing every sample twice;
+//   * d ring of 48 slots fed in 16-sample chunks (6 KB instead of 8; refill keeps 33..48 samples ahead of the AGC,
+//     always more than the longest segment of 24);
+//   * <= 144 registers (half the DC prefetch state of the 32-sample chunks).
+// Same arithmetic, same rounds, same parking rules as same_rx_fast_kernel; state hand-over identical.
+// ----------------------------------------------------------------------------------------------------------------
+#define DN_CHUNK 16
+#define DN_DRING 48
+#define DN_DBYTES (DN_DRING * 128)
+#define DN_BLOCKS 14
+#define DN_MAXREG 144      // 65536 registers / (14 blocks x 32 threads), allocation granularity 8
+
+__global__ void __maxnreg__(DN_MAXREG) same_rx_dense_kernel(const __grid_constant__ SameParams p,
+                                                                      const __grid_constant__ SameTaps2 taps,
+                                                                      const int16_t* __restrict__ samples,
+                                                                      const unsigned long long* __restrict__ offsets,
+                                                                      const uint32_t* __restrict__ lengths,
+                                                                      const uint32_t lanes) {
+  __shared__ float dring[DN_DRING * 32];
+  __shared__ float yring[FAST_RING * 32];
+  __shared__ float4 tapsm[FAST_NTAPS];
+
+  const SameLayout& L = p.layout;
+  const int lane = threadIdx.x;
+  const uint32_t s = blockIdx.x * lanes + lane;
+  const bool valid = (uint32_t)lane < lanes && s < p.n_streams;
+  const uint32_t sidx = valid ? s : 0u;
+  uint32_t* st = p.state32 + sidx;
+  StreamBlob* blob = p.blobs + sidx;
+
+  const uint32_t len = valid ? lengths[s] : 0u;
+  if (__all_sync(0xffffffffu, len == 0u)) return;
+  const int16_t* src = (samples != nullptr && valid) ? samples + offsets[s] : nullptr;
+
+  Lane a;
+  lane_load(a, p, st, s);
+  DcInt dc;
+  RawFeedT<DN_CHUNK> feed;
+  dc_load(dc, st, L);
+  feed.init(src, 0u, len);
+  for (int i = 0; i < DN_DRING; ++i) dring[i * 32 + lane] = 0.0f;   // stale slots are read, never used: keep them finite
+  for (int i = 0; i < FAST_RING; ++i) yring[i * 32 + lane] = 0.0f;
+  for (int i = 0; i < FAST_NTAPS; ++i)                               // demod window -> y ring slots of samples -42..-1
+    yring[((i - FAST_NTAPS) & (FAST_RING - 1)) * 32 + lane] = __uint_as_float(LANE_ST(st, L, L.win + i));
+  for (int i = lane; i < FAST_NTAPS; i += 32)
+    tapsm[i] = make_float4(taps.mark[i].x, taps.mark[i].y, taps.space[i].x, taps.space[i].y);
+  __syncwarp();
+
+  const float bw = p.agc_bw, gmin = p.agc_min, gmax = p.agc_max;
+  const float2 one2 = make_float2(p.f_one, p.f_one), negz2 = make_float2(p.f_negzero, p.f_negzero);
+  const uint32_t d_lane = smem_u32(dring) + ((uint32_t)lane << 2);
+  const uint32_t y_lane = smem_u32(yring) + ((uint32_t)lane << 2);
+
+  uint32_t pos = 0, rp = 0;
+  uint32_t pslot = 0, rslot = 0;     // d ring byte offsets (slot * 128) of pos and rp: the ring is not a power of two
+  bool dc_windows_stored = false;
+  int cfire = fire_clock(a.until, a.clock);
+  uint32_t pend = 0;                 // byte-phase / TED-phase alignment: see same_rx_fast_kernel
+  uint32_t round_ctr = 0;
+
+  while (__any_sync(0xffffffffu, pos < len || pend != 0u)) {
+    round_ctr += 1;
+    const bool byte_round = (round_ctr & 15u) == 0u;
+    // ---------------- refill (A0, A1): every lane with room for 16 samples takes them when any lane runs low ----------------
+    while (__any_sync(0xffffffffu, (rp - pos) <= (uint32_t)(DN_DRING - DN_CHUNK) && rp < len && pend == 0u)) {
+      const bool take = (rp < len) && (rp - pos) <= (uint32_t)(DN_DRING - DN_CHUNK);
+      const uint32_t nnew = take ? min((uint32_t)DN_CHUNK, len - rp) : 0u;
+      const uint32_t dst = d_lane + rslot;        // rp % 16 == 0 and 48 % 16 == 0: the chunk never wraps
+      if (nnew == DN_CHUNK) {
+        uint32_t cur[DN_CHUNK / 2];
+        feed.take_full(cur, rp, len);
+        dc_chunk<DN_CHUNK>(dc, cur, [&](int i, float d) { sts_f32(dst + (uint32_t)(i * 128), d); });
+        rp += DN_CHUNK;
+        rslot = (rslot + DN_CHUNK * 128 == DN_DBYTES) ? 0u : rslot + DN_CHUNK * 128;
+      } else if (nnew) {
+        uint32_t cur[DN_CHUNK / 2];
+        feed.take_partial(cur, rp, nnew);
+        dc_chunk_partial<DN_CHUNK>(dc, cur, (int)nnew, [&](int i, float d) { sts_f32(dst + (uint32_t)(i * 128), d); });
+        dc_store_after_partial<DN_CHUNK>(dc, cur, nnew, DcToState{st, L});
+        dc_windows_stored = true;
+        rp += nnew;
+      }
+      __syncwarp();
+    }
+
+    // ---------------- segment: AGC over this lane's samples up to its next TED instant (A2, A3) ----------------
+    int nseg = 0;
+    if (pos < len && pend == 0u) nseg = min(cfire - a.clock, (int)(rp - pos));
+    if (((a.tedcnt ^ round_ctr) & 1u) != 0u) nseg = 0;   // TED-phase alignment
+    const int maxseg = __reduce_max_sync(0xffffffffu, nseg);
+    const int nmin = __reduce_min_sync(0xffffffffu, nseg);
+    const float bw_eff = (a.flags & FLAG_AGC_LOCKED) ? 0.0f : bw;   // (!locked as f32) * (1-|y|) * bw   agc.rs:74
+    {
+      float g = a.g;
+      uint32_t od = pslot, oy = (pos << 7) & 0x1f80u;
+      int k = 0;
+      for (; k + 4 <= nmin; k += 4) {
+        float dv[4]; uint32_t oo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          oo[j] = oy; dv[j] = lds_f32(d_lane + od);
+          od += 128u; od = (od == DN_DBYTES) ? 0u : od;
+          oy = (oy + 128u) & 0x1f80u;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sts_f32(y_lane + oo[j], agc_step(g, dv[j], bw_eff, gmin, gmax));   // demod.rs:177-179
+      }
+      for (; k < maxseg; k += 2) {
+        float dv[2]; uint32_t oo[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          oo[j] = oy; dv[j] = lds_f32(d_lane + od);
+          od += 128u; od = (od == DN_DBYTES) ? 0u : od;
+          oy = (oy + 128u) & 0x1f80u;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const bool act = (k + j) < nseg;
+          const float y = agc_step(g, dv[j], act ? bw_eff : 0.0f, gmin, gmax);
+          if (act) sts_f32(y_lane + oo[j], y);
+        }
+      }
+      a.g = g;
+    }
+    pos += (uint32_t)nseg;
+    pslot += (uint32_t)nseg << 7;
+    pslot = (pslot >= DN_DBYTES) ? pslot - DN_DBYTES : pslot;
+    a.clock += nseg;
+    const bool fire = (nseg > 0) && (a.clock == cfire);
+    bool have_sym = false;
+    if (__any_sync(0xffffffffu, fire)) {
+      // ---------------- TED instant: matched filters (A4), every tap address wrapped into the 64-slot ring ----------------
+      float2 am = make_float2(0.0f, 0.0f), as = make_float2(0.0f, 0.0f);
+      const uint32_t e = ((pos - 1u) << 7) & 0x1f80u;
+#pragma unroll
+      for (int i = 0; i < FAST_NTAPS; ++i) {
+        const float v = lds_f32(y_lane + ((e - (uint32_t)(i << 7)) & 0x1f80u));
+        const float4 t = tapsm[i];
+        const float2 vv = make_float2(v, v);
+        am = __ffma2_rn(am, one2, __ffma2_rn(vv, make_float2(t.x, t.y), negz2));     // filter.rs:363-377, see mf_soft
+        as = __ffma2_rn(as, one2, __ffma2_rn(vv, make_float2(t.z, t.w), negz2));
+      }
+      const float soft = rclamp(FSUB(hypot_fixed(am.x, am.y), hypot_fixed(as.x, as.y)), -1.0f, 1.0f);  // demod.rs:163
+      if (fire) {
+        const float rem = FSUB(a.until, (float)a.clock);  // receiver.rs:352
+        a.clock = 0;
+        have_sym = ted_step(a, p, soft, rem);
+        cfire = fire_clock(a.until, 0);
+      }
+    }
+    // ---------------- symbol: squelch now (A6), byte path (A7-A9) on the aligned rounds ----------------
+    if (have_sym) pend = symbol_squelch(a, p, s, st, blob, a.ted1, a.ted2, a.n0 + pos);
+    if (byte_round && __any_sync(0xffffffffu, pend != 0u)) {
+      if (pend != 0u) {
+        symbol_byte(a, p, s, st, blob, (pend & SYM_ADJUSTED) != 0u, a.n0 + pos);
+        pend = 0u;
+      }
+    }
+  }
+
+  if (!valid || len == 0u) return;
+  lane_store(a, p, st, a.n0 + len);
+  if (!dc_windows_stored) dc_store(dc, DcToState{st, L});
+  for (int i = 0; i < FAST_NTAPS; ++i)
+    LANE_ST(st, L, L.win + i) = __float_as_uint(yring[((int)(len + i - FAST_NTAPS) & (FAST_RING - 1)) * 32 + lane]);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
 // Front-end kernel (feed-forward stages A0 + A1, time-parallel): s16 stream-major -> exact DC-blocked f32 in lane-major
 // tiles  d[(tile * n_max + n) * 32 + lane],  tile = 32 consecutive streams — one 128-byte line per (tile, sample), the
 // layout a warp of the loop kernel reads with one coalesced request.  HBM-bound: 2 B read + 4 B written per sample.
@@ -658,20 +836,20 @@ __global__ void __launch_bounds__(FE_WARPS * 32) same_frontend_kernel(const __gr
     dc_zero(dc);
     feed.init(src, r0 - FAST_CHUNK, len);
     feed.take_full(cur, r0 - FAST_CHUNK, len);
-    dc_chunk(dc, cur, [](int, float) {});          // warm-up: exact from the 32nd sample on
+    dc_chunk<FAST_CHUNK>(dc, cur, [](int, float) {});          // warm-up: exact from the 32nd sample on
   }
   float* dst = tiles.d + ((size_t)tile * tiles.n_max + r0) * 32u + (uint32_t)lane;
   uint32_t c = r0;
   for (; c + FAST_CHUNK <= r1; c += FAST_CHUNK, dst += FAST_CHUNK * 32) {
     feed.take_full(cur, c, len);
-    dc_chunk(dc, cur, [&](int i, float d) { __stcs(dst + i * 32, d); });
+    dc_chunk<FAST_CHUNK>(dc, cur, [&](int i, float d) { __stcs(dst + i * 32, d); });
   }
   const auto to_next = [&](uint32_t w, uint32_t bits) { tiles.dc_next[(size_t)w * L.n_pad + s] = bits; };
   if (c < r1) {                                      // r1 == len: the partial tail of the chunk
     const uint32_t nnew = r1 - c;
     feed.take_partial(cur, c, nnew);
-    dc_chunk_partial(dc, cur, (int)nnew, [&](int i, float d) { __stcs(dst + i * 32, d); });
-    dc_store_after_partial(dc, cur, nnew, to_next);
+    dc_chunk_partial<FAST_CHUNK>(dc, cur, (int)nnew, [&](int i, float d) { __stcs(dst + i * 32, d); });
+    dc_store_after_partial<FAST_CHUNK>(dc, cur, nnew, to_next);
   } else if (r1 == len) {
     dc_store(dc, to_next);
   }
@@ -735,13 +913,13 @@ __device__ __forceinline__ void ws_producer(const SameParams& p, uint32_t* st, c
     if (nnew == FAST_CHUNK) {
       uint32_t cur[FAST_CHUNK / 2];
       feed.take_full(cur, rp, len);
-      dc_chunk(dc, cur, [&](int i, float d) { dst[i * 32] = d; });
+      dc_chunk<FAST_CHUNK>(dc, cur, [&](int i, float d) { dst[i * 32] = d; });
       rp += FAST_CHUNK;
     } else if (nnew) {
       uint32_t cur[FAST_CHUNK / 2];
       feed.take_partial(cur, rp, nnew);
-      dc_chunk_partial(dc, cur, (int)nnew, [&](int i, float d) { dst[i * 32] = d; });
-      dc_store_after_partial(dc, cur, nnew, DcToState{st, L});   // final DC windows, back in canonical order
+      dc_chunk_partial<FAST_CHUNK>(dc, cur, (int)nnew, [&](int i, float d) { dst[i * 32] = d; });
+      dc_store_after_partial<FAST_CHUNK>(dc, cur, nnew, DcToState{st, L});   // final DC windows, back in canonical order
       dc_windows_stored = true;
       rp += nnew;
     }
@@ -1270,7 +1448,7 @@ __global__ void same_evsort_scatter(const same_event* __restrict__ ev, uint32_t 
 // Launchers (called from same_engine.cu)
 // ----------------------------------------------------------------------------------------------------------------
 // kernel ids: 1 generic, 2 single-warp fast, 3 pipelined four-warp, 4 three-warp, 5 single-warp fast fed by the front-end
-// kernel's tiles (split pipeline).  `fast_variant`: 0 = y ring with mirror slots, 1 = without (more resident warps).
+// kernel's tiles (split pipeline), 6 dense single-warp (14 resident blocks per SM).  `fast_variant`: 0 = y ring with mirror slots, 1 = without (more resident warps).
 extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps, const SameTaps2* taps2, int force_generic,
                                       uint32_t lanes_per_warp, const void* d_samples_v, int sample_fmt,
                                       const unsigned long long* d_offsets, const uint32_t* d_lengths,
@@ -1292,6 +1470,8 @@ extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps,
         same_dev::same_rx_fast_kernel<true, false, 12><<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes, t);
       else
         same_dev::same_rx_fast_kernel<true, true, 1><<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes, t);
+    } else if (force_generic == 6) {
+      same_dev::same_rx_dense_kernel<<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes);
     } else if (force_generic == 2) {
       if (fast_variant == 1)
         same_dev::same_rx_fast_kernel<false, false, 12><<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes, t);

@@ -41,9 +41,11 @@ def main():
         rx = sb.SameReceiverBuilder.samedec(RATE).build_batch(ns)
         out = {"streams": ns, "seconds": secs, "samples": ns * n, "policy_kernel": rx.get_option("kernel_selected")}
         ref = None
-        for name, kernel, variant in (("fused_single_warp_mirror", 2, 0), ("fused_single_warp_nomirror", 2, 1),
-                                      ("fused_three_warp", 4, 0), ("fused_pipelined", 3, 0),
-                                      ("split_frontend_plus_tilefed", 5, 0), ("split_frontend_plus_tilefed_nomirror", 5, 1)):
+        cases = [("fused_single_warp", 2, 0), ("fused_dense", 6, 0), ("fused_three_warp", 4, 0), ("fused_pipelined", 3, 0),
+                 ("split_frontend_plus_tilefed", 5, 0)]
+        if "--quick" in sys.argv:
+            cases = cases[:2]
+        for name, kernel, variant in cases:
             rx.set_option("kernel", kernel)
             rx.set_option("fast_variant", variant)
             best = None
