@@ -197,8 +197,8 @@ int same_engine_read_soft_trace(same_engine* e, uint32_t stream, same_soft_symbo
  *                     22050 Hz fast kernels apply; 2 single-warp fast kernel; 3 four-warp pipelined kernel;
  *                     4 three-warp kernel; 5 split pipeline: the time-parallel front-end kernel (s16 -> exact DC-blocked
  *                     f32 tiles, HBM-bound) followed by the single-warp kernel fed from those tiles -- the measured
- *                     alternative to the fused kernels.  ("force_generic": old name.)
- *   "fast_variant"    single-warp kernel's window ring: 0 with mirror slots (default), 1 without (more resident warps)
+ *                     alternative to the fused kernels; 6 look-ahead single-warp kernel (throughput
+ *                     regime: 16 resident warps per SM).  ("force_generic": old name.)
  *   "lanes_per_warp"  streams per warp of the fast kernels (1, 2, 4, 8, 16, 32)
  *   "device_sort"     1 (default): big batches of events are put into per-stream order on the device before the
  *                     read-back; 0: always on the host

@@ -19,7 +19,7 @@
 extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps, const SameTaps2* taps2, int force_generic,
                                       uint32_t lanes_per_warp, const void* d_samples, int sample_fmt,
                                       const unsigned long long* d_offsets, const uint32_t* d_lengths,
-                                      const SameTiles* tiles, int fast_variant, cudaStream_t stream);
+                                      const SameTiles* tiles, cudaStream_t stream);
 extern "C" cudaError_t same_launch_frontend(const SameParams* p, const int16_t* d_samples, const unsigned long long* d_offsets,
                                             const uint32_t* d_lengths, const SameTiles* tiles, cudaStream_t stream);
 extern "C" cudaError_t same_launch_evsort(const same_event* d_events, uint32_t n, uint32_t n_streams, uint32_t* d_cnt,
@@ -85,7 +85,6 @@ struct same_engine {
   uint32_t lanes_per_warp = 32;   // streams per warp in the fast kernel (lane-sparse warps for small batches)
   int sm_count = 148;
   int kernel_auto = 0;            // fast-kernel flavour when force_generic == 0: 3 pipelined, 4 three-warp, 2 single-warp
-  int fast_variant = 0;           // option "fast_variant": y ring of the single-warp kernel with (0) / without (1) mirror slots
   SameTiles tiles{nullptr, nullptr, 0u};   // split pipeline (kernel 5): front-end output, allocated on first use
   size_t tiles_cap = 0;           // floats
   bool saw_f32 = false;           // an f32 submit happened since create / reset(all): DC state may be non-integer -> generic kernel
@@ -330,7 +329,7 @@ int submit_common(same_engine* e, const void* host_samples, const void* dev_samp
     }
   }
   CK(e, same_launch_rx(&e->p, &e->taps, &e->taps2, kernel, e->lanes_per_warp, d_src, sample_fmt, b.d_off, b.d_len, &e->tiles,
-                       e->fast_variant, e->compute));
+                       e->compute));
   CK(e, cudaEventRecord(e->t_k1, e->compute));
   CK(e, cudaEventRecord(b.consumed, e->compute));
   b.used = true;
@@ -810,15 +809,11 @@ int same_engine_set_option(same_engine* e, const char* key, int value) {
   int rc = same_engine_sync(e);
   if (rc) return rc;
   if (strcmp(key, "kernel") == 0 || strcmp(key, "force_generic") == 0) {
-    if (value < 0 || value > 6) return fail(e, SAME_ERR_INVALID_ARG, "kernel must be 0 (policy), 1 generic, 2 single-warp, 3 pipelined, 4 three-warp, 5 split (front end + tile-fed) or 6 dense single-warp");
+    if (value < 0 || value > 6) return fail(e, SAME_ERR_INVALID_ARG, "kernel must be 0 (policy), 1 generic, 2 single-warp, 3 pipelined, 4 three-warp, 5 split (front end + tile-fed) or 6 look-ahead single-warp");
     e->force_generic = value;
     return SAME_OK;
   }
-  if (strcmp(key, "fast_variant") == 0) {
-    if (value < 0 || value > 1) return fail(e, SAME_ERR_INVALID_ARG, "fast_variant must be 0 or 1");
-    e->fast_variant = value;
-    return SAME_OK;
-  }
+
   if (strcmp(key, "device_sort") == 0) { e->device_sort = value != 0; return SAME_OK; }
   if (strcmp(key, "lanes_per_warp") == 0) {
     if (!(value == 1 || value == 2 || value == 4 || value == 8 || value == 16 || value == 32))
@@ -834,7 +829,6 @@ int same_engine_get_option(same_engine* e, const char* key, int* value) {
   if (strcmp(key, "kernel") == 0 || strcmp(key, "force_generic") == 0) { *value = e->force_generic; return SAME_OK; }
   if (strcmp(key, "device_sort") == 0) { *value = e->device_sort; return SAME_OK; }
   if (strcmp(key, "lanes_per_warp") == 0) { *value = (int)e->lanes_per_warp; return SAME_OK; }
-  if (strcmp(key, "fast_variant") == 0) { *value = e->fast_variant; return SAME_OK; }
   if (strcmp(key, "kernel_selected") == 0) {
     const bool fast_geometry = e->p.ntaps == 42 && e->p.dc_len == 16;
     *value = (e->saw_f32 || !fast_geometry) ? 1 : (e->force_generic ? e->force_generic : e->kernel_auto);

@@ -386,9 +386,9 @@ __device__ __forceinline__ float agc_step(float& g, const float d, const float b
 // Every lane runs the warp's longest trip count.  Samples k0 .. nmin-1 (nmin = warp minimum) need no predicate; in the
 // short tail, samples beyond a lane's own segment use bandwidth 0 (g + t*0 == g exactly; the stale d they read is
 // finite) and store nothing.  The d loads of a group are issued together so that their latency is paid once per group.
-// od / oy: byte offsets ((slot * 128) | lane * 4) of sample k0 in the d ring (mask DMASK) and the y ring (64 slots;
-// MIRROR: each y is stored at slot j and at its mirror j + 64).
-template <uint32_t DMASK, bool MIRROR>
+// od / oy: byte offsets ((slot * 128) | lane * 4) of sample k0 in the d ring (mask DMASK) and the y ring (64 slots,
+// each y stored at slot j and at its mirror j + 64).
+template <uint32_t DMASK>
 __device__ __forceinline__ float agc_segment(float g, const float bw_eff, const float gmin, const float gmax,
                                              const uint32_t d_base, const uint32_t y_base, uint32_t od, uint32_t oy, int k,
                                              const int nmin, const int maxseg, const int nseg) {
@@ -404,7 +404,7 @@ __device__ __forceinline__ float agc_segment(float g, const float bw_eff, const 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float y = agc_step(g, dv[j], bw_eff, gmin, gmax);
-      if (MIRROR) sts_f32_mirrored(y_base + oo[j], y); else sts_f32(y_base + oo[j], y);    // demod.rs:177-179
+      sts_f32_mirrored(y_base + oo[j], y);                                              // demod.rs:177-179
     }
   }
   for (; k < maxseg; k += 2) {
@@ -419,7 +419,7 @@ __device__ __forceinline__ float agc_segment(float g, const float bw_eff, const 
     for (int j = 0; j < 2; ++j) {
       const bool act = (k + j) < nseg;
       const float y = agc_step(g, dv[j], act ? bw_eff : 0.0f, gmin, gmax);
-      if (act) { if (MIRROR) sts_f32_mirrored(y_base + oo[j], y); else sts_f32(y_base + oo[j], y); }
+      if (act) sts_f32_mirrored(y_base + oo[j], y);
     }
   }
   return g;
@@ -428,52 +428,36 @@ __device__ __forceinline__ float agc_segment(float g, const float bw_eff, const 
 // Matched filters (A4) at the sample that ends at ring position `end` (exclusive), packed exact f32 ops:
 // fma(v, h, -0) == RN(v*h) and fma(acc, 1, prod) == RN(acc + prod): two separately rounded operations per tap and
 // accumulator, as filter.rs:363-377 requires.  The -0 and 1 operands are run-time values (SameParams) so that ptxas
-// cannot fold the pair back into one fused multiply-add.  MIRROR: the window is read at descending static offsets
-// from its newest slot (never wraps); otherwise every tap address is wrapped into the 64-slot ring.
-template <bool MIRROR>
+// cannot fold the pair back into one fused multiply-add.  The window is read at descending static offsets from its
+// newest slot in the mirrored ring (never wraps).
 __device__ __forceinline__ float mf_soft(const float* yring, const float4* tapsm, const int lane, const uint32_t end,
                                          const float2 one2, const float2 negz2) {
   float2 am = make_float2(0.0f, 0.0f), as = make_float2(0.0f, 0.0f);
-  if (MIRROR) {
-    int nslot = (int)((end - 1u) & (FAST_RING - 1));
-    if (nslot < FAST_NTAPS - 1) nslot += FAST_RING;
-    const float* yp = yring + nslot * 32 + lane;
+  int nslot = (int)((end - 1u) & (FAST_RING - 1));
+  if (nslot < FAST_NTAPS - 1) nslot += FAST_RING;
+  const float* yp = yring + nslot * 32 + lane;
 #pragma unroll
-    for (int i = 0; i < FAST_NTAPS; ++i) {
-      const float v = yp[-i * 32];
-      const float4 t = tapsm[i];
-      const float2 vv = make_float2(v, v);
-      am = __ffma2_rn(am, one2, __ffma2_rn(vv, make_float2(t.x, t.y), negz2));
-      as = __ffma2_rn(as, one2, __ffma2_rn(vv, make_float2(t.z, t.w), negz2));
-    }
-  } else {
-    const uint32_t y_lane = smem_u32(yring) + ((uint32_t)lane << 2);
-    const uint32_t e = ((end - 1u) & (FAST_RING - 1)) << 7;
-#pragma unroll
-    for (int i = 0; i < FAST_NTAPS; ++i) {
-      const float v = lds_f32(y_lane + ((e - (uint32_t)(i << 7)) & 0x1f80u));
-      const float4 t = tapsm[i];
-      const float2 vv = make_float2(v, v);
-      am = __ffma2_rn(am, one2, __ffma2_rn(vv, make_float2(t.x, t.y), negz2));
-      as = __ffma2_rn(as, one2, __ffma2_rn(vv, make_float2(t.z, t.w), negz2));
-    }
+  for (int i = 0; i < FAST_NTAPS; ++i) {
+    const float v = yp[-i * 32];
+    const float4 t = tapsm[i];
+    const float2 vv = make_float2(v, v);
+    am = __ffma2_rn(am, one2, __ffma2_rn(vv, make_float2(t.x, t.y), negz2));
+    as = __ffma2_rn(as, one2, __ffma2_rn(vv, make_float2(t.z, t.w), negz2));
   }
   return rclamp(FSUB(hypot_fixed(am.x, am.y), hypot_fixed(as.x, as.y)), -1.0f, 1.0f);  // demod.rs:163
 }
 
 // TILE_FED: the DC-blocked samples come from same_frontend_kernel's lane-major f32 tiles instead of the fused integer
 // recursion (measured A/B of DESIGN.md §5; the kernel then only commits the front end's DC state).
-// MIRROR: y ring with mirror slots (static matched-filter addresses, 2 stores per sample, 16 KB) or without (8 KB,
-// wrapped addresses): smaller shared memory -> more resident warps.
-template <bool TILE_FED, bool MIRROR, int MIN_BLOCKS>
-__global__ void __launch_bounds__(32, MIN_BLOCKS) same_rx_fast_kernel(const __grid_constant__ SameParams p,
+template <bool TILE_FED>
+__global__ void __launch_bounds__(32, 8) same_rx_fast_kernel(const __grid_constant__ SameParams p,
                                                           const __grid_constant__ SameTaps2 taps,
                                                           const int16_t* __restrict__ samples,
                                                           const unsigned long long* __restrict__ offsets,
                                                           const uint32_t* __restrict__ lengths, const uint32_t lanes,
                                                           const SameTiles tiles) {
   __shared__ float dring[FAST_RING * 32];
-  __shared__ float yring[(MIRROR ? 2 : 1) * FAST_RING * 32];
+  __shared__ float yring[2 * FAST_RING * 32];
   __shared__ float4 tapsm[FAST_NTAPS];
 
   const SameLayout& L = p.layout;
@@ -501,12 +485,11 @@ __global__ void __launch_bounds__(32, MIN_BLOCKS) same_rx_fast_kernel(const __gr
   }
   // demod window -> y ring slots of samples -42..-1 (and mirrors); d ring starts finite (stale slots are read, never used)
   for (int i = 0; i < FAST_RING; ++i) dring[i * 32 + lane] = 0.0f;
-  if (!MIRROR) for (int i = 0; i < FAST_RING; ++i) yring[i * 32 + lane] = 0.0f;
   for (int i = 0; i < FAST_NTAPS; ++i) {
     const float v = __uint_as_float(LANE_ST(st, L, L.win + i));
     const int slot = (i - FAST_NTAPS) & (FAST_RING - 1);
     yring[slot * 32 + lane] = v;
-    if (MIRROR) yring[(slot + FAST_RING) * 32 + lane] = v;
+    yring[(slot + FAST_RING) * 32 + lane] = v;
   }
   for (int i = lane; i < FAST_NTAPS; i += 32)
     tapsm[i] = make_float4(taps.mark[i].x, taps.mark[i].y, taps.space[i].x, taps.space[i].y);
@@ -579,14 +562,14 @@ __global__ void __launch_bounds__(32, MIN_BLOCKS) same_rx_fast_kernel(const __gr
     const int nmin = __reduce_min_sync(0xffffffffu, nseg);
     const float bw_eff = (a.flags & FLAG_AGC_LOCKED) ? 0.0f : bw;   // (!locked as f32) * (1-|y|) * bw   agc.rs:74
     const uint32_t o = ((pos << 7) & 0x1f80u) | ((uint32_t)lane << 2);
-    a.g = agc_segment<0x1fffu, MIRROR>(a.g, bw_eff, gmin, gmax, d_base, y_base, o, o, 0, nmin, maxseg, nseg);
+    a.g = agc_segment<0x1fffu>(a.g, bw_eff, gmin, gmax, d_base, y_base, o, o, 0, nmin, maxseg, nseg);
     pos += (uint32_t)nseg;
     a.clock += nseg;
     const bool fire = (nseg > 0) && (a.clock == cfire);
     bool have_sym = false;
     if (__any_sync(0xffffffffu, fire)) {
       // ---------------- TED instant: matched filters (A4), timing loop (A5) ----------------
-      const float soft = mf_soft<MIRROR>(yring, tapsm, lane, pos, one2, negz2);
+      const float soft = mf_soft(yring, tapsm, lane, pos, one2, negz2);
       if (fire) {
         const float rem = FSUB(a.until, (float)a.clock);  // receiver.rs:352
         a.clock = 0;
@@ -621,32 +604,35 @@ __global__ void __launch_bounds__(32, MIN_BLOCKS) same_rx_fast_kernel(const __gr
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// Dense kernel: the single-warp fast kernel re-budgeted for RESIDENCY.  In the throughput regime every block lives for
-// the whole submit and a warp on its own issues only ~0.3 instructions per cycle (dependent AGC / accumulator chains),
-// so what matters is how many warps share a scheduler and that ALL blocks of the grid are resident at once: 65 536
-// streams are 2048 warps = 13.8 per SM, which at the fast kernel's 8 blocks per SM run as one wave of 8 and a tail wave
-// of 6 (measured: 0.49 issue slots used; profiles/ncu_r02_*).  This kernel fits DN_BLOCKS = 14 blocks per SM:
-//   * y ring without mirror slots (8 KB instead of 16): the matched filter wraps every tap address into the ring
-//     (2 integer ops per tap) instead of storing every sample twice;
-//   * d ring of 48 slots fed in 16-sample chunks (6 KB instead of 8; refill keeps 33..48 samples ahead of the AGC,
-//     always more than the longest segment of 24);
-//   * <= 144 registers (half the DC prefetch state of the 32-sample chunks).
-// Same arithmetic, same rounds, same parking rules as same_rx_fast_kernel; state hand-over identical.
+// Look-ahead kernel: the single-warp receiver for the THROUGHPUT regime (many more warps than schedulers).
+//
+// What the profiles of same_rx_fast_kernel say (profiles/ncu_r02_fast_65536x5.*): 57.7 warp-instructions per sample, but
+// only 0.49 issue slots used, because each SM sub-partition holds two warps (254 registers, 25 KB of shared memory per
+// warp) and one warp on its own issues 0.3 instructions per cycle (dependent AGC and accumulator chains).  Residency
+// comes in steps of four warps per SM (the register file is split over the four sub-partitions): 16 resident warps need
+// <= 128 registers and <= 13.2 KB per warp.  This kernel gets there by dropping the d ring and the mirror slots:
+//   * The AGC no longer waits for the timing loop.  It depends on the rest of the receiver only through the lock flag
+//     (agc.rs:74), so DC blocker and AGC run together in static 8-sample chunks (one 16-byte load), straight from
+//     registers into the y ring, until they have passed the lane's next TED instant — at most 7 samples of look-ahead.
+//     The look-ahead is exact speculation: if the symbol stages at that instant flip the lock flag, the tail of the last
+//     chunk is recomputed from its saved inputs (d values, starting gain, per-sample flag mask).  No d ring, no
+//     per-sample loop of run-time length, and the independent DC arithmetic of later samples fills the issue slots
+//     under the gain chain.
+//   * DC-blocker history: the last 16 raw samples stay in registers (packed pairs), the last 16 values of S1 live in a
+//     2 KB shared-memory ring (static offsets from a per-chunk base).
+//   * y ring: 64 slots, no mirror (8 KB): the matched filter wraps every tap address into the ring.
+// Same arithmetic, same rounds, same parking rules and same resident state as the other fast kernels.
 // ----------------------------------------------------------------------------------------------------------------
-#define DN_CHUNK 16
-#define DN_DRING 48
-#define DN_DBYTES (DN_DRING * 128)
-#define DN_BLOCKS 14
-#define DN_MAXREG 144      // 65536 registers / (14 blocks x 32 threads), allocation granularity 8
+#define LA_CHUNK 8
+#define LA_MAXREG 128
 
-__global__ void __maxnreg__(DN_MAXREG) same_rx_dense_kernel(const __grid_constant__ SameParams p,
-                                                                      const __grid_constant__ SameTaps2 taps,
-                                                                      const int16_t* __restrict__ samples,
-                                                                      const unsigned long long* __restrict__ offsets,
-                                                                      const uint32_t* __restrict__ lengths,
-                                                                      const uint32_t lanes) {
-  __shared__ float dring[DN_DRING * 32];
+__global__ void __maxnreg__(LA_MAXREG) same_rx_la_kernel(const __grid_constant__ SameParams p,
+                                                         const __grid_constant__ SameTaps2 taps,
+                                                         const int16_t* __restrict__ samples,
+                                                         const unsigned long long* __restrict__ offsets,
+                                                         const uint32_t* __restrict__ lengths, const uint32_t lanes) {
   __shared__ float yring[FAST_RING * 32];
+  __shared__ int s1ring[FAST_DCL * 32];
   __shared__ float4 tapsm[FAST_NTAPS];
 
   const SameLayout& L = p.layout;
@@ -660,16 +646,25 @@ __global__ void __maxnreg__(DN_MAXREG) same_rx_dense_kernel(const __grid_constan
   const uint32_t len = valid ? lengths[s] : 0u;
   if (__all_sync(0xffffffffu, len == 0u)) return;
   const int16_t* src = (samples != nullptr && valid) ? samples + offsets[s] : nullptr;
+  const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
 
   Lane a;
   lane_load(a, p, st, s);
-  DcInt dc;
-  RawFeedT<DN_CHUNK> feed;
-  dc_load(dc, st, L);
-  feed.init(src, 0u, len);
-  for (int i = 0; i < DN_DRING; ++i) dring[i * 32 + lane] = 0.0f;   // stale slots are read, never used: keep them finite
+
+  // ---- DC blocker state as integers (see DcInt): sums and raw history in registers, S1 history in shared memory ----
+  int S1 = __float2int_rn(__uint_as_float(LANE_ST(st, L, F_DC_FFSUM)));
+  int S2 = __float2int_rn(__uint_as_float(LANE_ST(st, L, F_DC_FBSUM)) * 16.0f);
+  uint32_t rawh[FAST_DCL / 2];
+#pragma unroll
+  for (int i = 0; i < FAST_DCL / 2; ++i) {
+    const int lo = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_ff + 2 * i)));
+    const int hi = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_ff + 2 * i + 1)));
+    rawh[i] = ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16);
+  }
+  for (int i = 0; i < FAST_DCL; ++i)     // the S1 of sample n lives in slot n & 15: samples -16..-1 -> slots 0..15
+    s1ring[i * 32 + lane] = __float2int_rn(__uint_as_float(LANE_ST(st, L, L.dc_fb + i)) * 16.0f);
   for (int i = 0; i < FAST_RING; ++i) yring[i * 32 + lane] = 0.0f;
-  for (int i = 0; i < FAST_NTAPS; ++i)                               // demod window -> y ring slots of samples -42..-1
+  for (int i = 0; i < FAST_NTAPS; ++i)   // demod window -> y ring slots of samples -42..-1
     yring[((i - FAST_NTAPS) & (FAST_RING - 1)) * 32 + lane] = __uint_as_float(LANE_ST(st, L, L.win + i));
   for (int i = lane; i < FAST_NTAPS; i += 32)
     tapsm[i] = make_float4(taps.mark[i].x, taps.mark[i].y, taps.space[i].x, taps.space[i].y);
@@ -677,96 +672,124 @@ __global__ void __maxnreg__(DN_MAXREG) same_rx_dense_kernel(const __grid_constan
 
   const float bw = p.agc_bw, gmin = p.agc_min, gmax = p.agc_max;
   const float2 one2 = make_float2(p.f_one, p.f_one), negz2 = make_float2(p.f_negzero, p.f_negzero);
-  const uint32_t d_lane = smem_u32(dring) + ((uint32_t)lane << 2);
   const uint32_t y_lane = smem_u32(yring) + ((uint32_t)lane << 2);
+  const uint32_t s1_lane = smem_u32(s1ring) + ((uint32_t)lane << 2);
 
-  uint32_t pos = 0, rp = 0;
-  uint32_t pslot = 0, rslot = 0;     // d ring byte offsets (slot * 128) of pos and rp: the ring is not a power of two
+  uint32_t pos = 0;        // samples consumed by the timing loop
+  uint32_t rp = 0;         // samples through DC blocker + AGC (pos <= rp <= pos + 7 between rounds)
+  float g = a.g;           // AGC gain after sample rp - 1
+  // the last chunk, kept for the exact redo after a lock flip: inputs, gain before it, per-sample lock flags, length
+  float dlast[LA_CHUNK];
+#pragma unroll
+  for (int i = 0; i < LA_CHUNK; ++i) dlast[i] = 0.0f;
+  float g0 = g;
+  uint32_t lockmask = 0, nlast = 0;
   bool dc_windows_stored = false;
+  int4 nx = make_int4(0, 0, 0, 0);
+  bool pf_ok = src != nullptr && aligned && len >= (uint32_t)LA_CHUNK;
+  if (pf_ok) nx = __ldg(reinterpret_cast<const int4*>(src));
+
   int cfire = fire_clock(a.until, a.clock);
-  uint32_t pend = 0;                 // byte-phase / TED-phase alignment: see same_rx_fast_kernel
+  uint32_t pend = 0;       // byte-phase / TED-phase alignment: see same_rx_fast_kernel
   uint32_t round_ctr = 0;
 
   while (__any_sync(0xffffffffu, pos < len || pend != 0u)) {
     round_ctr += 1;
     const bool byte_round = (round_ctr & 15u) == 0u;
-    // ---------------- refill (A0, A1): every lane with room for 16 samples takes them when any lane runs low ----------------
-    while (__any_sync(0xffffffffu, (rp - pos) <= (uint32_t)(DN_DRING - DN_CHUNK) && rp < len && pend == 0u)) {
-      const bool take = (rp < len) && (rp - pos) <= (uint32_t)(DN_DRING - DN_CHUNK);
-      const uint32_t nnew = take ? min((uint32_t)DN_CHUNK, len - rp) : 0u;
-      const uint32_t dst = d_lane + rslot;        // rp % 16 == 0 and 48 % 16 == 0: the chunk never wraps
-      if (nnew == DN_CHUNK) {
-        uint32_t cur[DN_CHUNK / 2];
-        feed.take_full(cur, rp, len);
-        dc_chunk<DN_CHUNK>(dc, cur, [&](int i, float d) { sts_f32(dst + (uint32_t)(i * 128), d); });
-        rp += DN_CHUNK;
-        rslot = (rslot + DN_CHUNK * 128 == DN_DBYTES) ? 0u : rslot + DN_CHUNK * 128;
-      } else if (nnew) {
-        uint32_t cur[DN_CHUNK / 2];
-        feed.take_partial(cur, rp, nnew);
-        dc_chunk_partial<DN_CHUNK>(dc, cur, (int)nnew, [&](int i, float d) { sts_f32(dst + (uint32_t)(i * 128), d); });
-        dc_store_after_partial<DN_CHUNK>(dc, cur, nnew, DcToState{st, L});
-        dc_windows_stored = true;
-        rp += nnew;
+    int nseg = 0;
+    if (pos < len && pend == 0u) nseg = min(cfire - a.clock, (int)(len - pos));
+    if (((a.tedcnt ^ round_ctr) & 1u) != 0u) nseg = 0;   // TED-phase alignment
+    const uint32_t target = pos + (uint32_t)nseg;
+
+    // ---------------- DC blocker + AGC in 8-sample chunks until this lane's target is covered (A0-A3) ----------------
+    while (__any_sync(0xffffffffu, rp < target)) {
+      if (rp < target) {
+        const uint32_t nnew = min((uint32_t)LA_CHUNK, len - rp);
+        const bool locked = (a.flags & FLAG_AGC_LOCKED) != 0u;
+        const float bw_eff = locked ? 0.0f : bw;           // (!locked as f32) * (1-|y|) * bw   agc.rs:74
+        const uint32_t ys = y_lane + ((rp & (FAST_RING - 1)) << 7);   // rp % 8 == 0: a chunk never wraps in either ring
+        const uint32_t ss = s1_lane + ((rp & (FAST_DCL - 1)) << 7);
+        uint32_t cur[LA_CHUNK / 2];
+        g0 = g; lockmask = locked ? 0xffu : 0u; nlast = nnew;
+        if (nnew == LA_CHUNK) {
+          if (pf_ok) { cur[0] = nx.x; cur[1] = nx.y; cur[2] = nx.z; cur[3] = nx.w; }
+          else {
+#pragma unroll
+            for (int i = 0; i < LA_CHUNK / 2; ++i) {
+              const uint32_t lo = src ? (uint32_t)(uint16_t)src[rp + 2 * i] : 0u;
+              const uint32_t hi = src ? (uint32_t)(uint16_t)src[rp + 2 * i + 1] : 0u;
+              cur[i] = lo | (hi << 16);
+            }
+          }
+          pf_ok = src != nullptr && aligned && (len - rp) >= 2u * LA_CHUNK;
+          if (pf_ok) nx = __ldg(reinterpret_cast<const int4*>(src + rp + LA_CHUNK));
+#pragma unroll
+          for (int i = 0; i < LA_CHUNK; ++i) {
+            const int x = s16_at(cur, i), x16 = s16_at(rawh, i), x15 = s16_at(rawh, i + 1);
+            S1 += x - x16;                                         // dcblock.rs:106 (ff)
+            int s1old;
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(s1old) : "r"(ss + (uint32_t)(i << 7)));
+            S2 += S1 - s1old;                                      // dcblock.rs:106 (fb)
+            asm volatile("st.shared.s32 [%0], %1;" ::"r"(ss + (uint32_t)(i << 7)), "r"(S1) : "memory");
+            const float d = (float)((x15 << 8) - S2) * 0.00390625f;  // dcblock.rs:48
+            dlast[i] = d;
+            sts_f32(ys + (uint32_t)(i << 7), agc_step(g, d, bw_eff, gmin, gmax));   // agc.rs:72-77, demod.rs:177-179
+          }
+#pragma unroll
+          for (int i = 0; i < FAST_DCL / 4; ++i) { rawh[i] = rawh[i + FAST_DCL / 4]; rawh[i + FAST_DCL / 4] = cur[i]; }
+          rp += LA_CHUNK;
+        } else {
+          // ---- the final, partial chunk of this submit: scalar loads, per-sample predicates; the DC windows are final
+          // and go to the state words right here, rotated back into canonical order (oldest first) ----
+#pragma unroll
+          for (int i = 0; i < LA_CHUNK / 2; ++i) cur[i] = 0u;
+#pragma unroll
+          for (int i = 0; i < LA_CHUNK; ++i) {
+            const uint32_t v = (src && i < (int)nnew) ? (uint32_t)(uint16_t)src[rp + i] : 0u;
+            cur[i >> 1] |= (i & 1) ? (v << 16) : v;
+          }
+#pragma unroll
+          for (int i = 0; i < LA_CHUNK; ++i) {
+            if (i < (int)nnew) {
+              const int x = s16_at(cur, i), x16 = s16_at(rawh, i), x15 = s16_at(rawh, i + 1);
+              S1 += x - x16;
+              const int s1old = s1ring[((rp + i) & (FAST_DCL - 1)) * 32 + lane];
+              S2 += S1 - s1old;
+              s1ring[((rp + i) & (FAST_DCL - 1)) * 32 + lane] = S1;
+              const float d = (float)((x15 << 8) - S2) * 0.00390625f;
+              dlast[i] = d;
+              sts_f32(ys + (uint32_t)(i << 7), agc_step(g, d, bw_eff, gmin, gmax));
+            }
+          }
+          // ff window = the last 16 of (rawh ++ cur[0..nnew)); static register indices, run-time word numbers
+#pragma unroll
+          for (int i = 0; i < FAST_DCL; ++i)
+            if (i >= (int)nnew) LANE_ST(st, L, L.dc_ff + ((uint32_t)i - nnew)) = __float_as_uint((float)s16_at(rawh, i));
+#pragma unroll
+          for (int i = 0; i < LA_CHUNK; ++i)
+            if (i < (int)nnew) LANE_ST(st, L, L.dc_ff + ((uint32_t)(FAST_DCL + i) - nnew)) = __float_as_uint((float)s16_at(cur, i));
+          dc_windows_stored = true;
+          rp += nnew;
+        }
       }
       __syncwarp();
     }
 
-    // ---------------- segment: AGC over this lane's samples up to its next TED instant (A2, A3) ----------------
-    int nseg = 0;
-    if (pos < len && pend == 0u) nseg = min(cfire - a.clock, (int)(rp - pos));
-    if (((a.tedcnt ^ round_ctr) & 1u) != 0u) nseg = 0;   // TED-phase alignment
-    const int maxseg = __reduce_max_sync(0xffffffffu, nseg);
-    const int nmin = __reduce_min_sync(0xffffffffu, nseg);
-    const float bw_eff = (a.flags & FLAG_AGC_LOCKED) ? 0.0f : bw;   // (!locked as f32) * (1-|y|) * bw   agc.rs:74
-    {
-      float g = a.g;
-      uint32_t od = pslot, oy = (pos << 7) & 0x1f80u;
-      int k = 0;
-      for (; k + 4 <= nmin; k += 4) {
-        float dv[4]; uint32_t oo[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          oo[j] = oy; dv[j] = lds_f32(d_lane + od);
-          od += 128u; od = (od == DN_DBYTES) ? 0u : od;
-          oy = (oy + 128u) & 0x1f80u;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) sts_f32(y_lane + oo[j], agc_step(g, dv[j], bw_eff, gmin, gmax));   // demod.rs:177-179
-      }
-      for (; k < maxseg; k += 2) {
-        float dv[2]; uint32_t oo[2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          oo[j] = oy; dv[j] = lds_f32(d_lane + od);
-          od += 128u; od = (od == DN_DBYTES) ? 0u : od;
-          oy = (oy + 128u) & 0x1f80u;
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const bool act = (k + j) < nseg;
-          const float y = agc_step(g, dv[j], act ? bw_eff : 0.0f, gmin, gmax);
-          if (act) sts_f32(y_lane + oo[j], y);
-        }
-      }
-      a.g = g;
-    }
-    pos += (uint32_t)nseg;
-    pslot += (uint32_t)nseg << 7;
-    pslot = (pslot >= DN_DBYTES) ? pslot - DN_DBYTES : pslot;
+    // ---------------- the timing loop's side: advance to the target, TED instant (A4, A5) ----------------
+    pos = target;
     a.clock += nseg;
     const bool fire = (nseg > 0) && (a.clock == cfire);
+    const uint32_t lock_before = a.flags & FLAG_AGC_LOCKED;
     bool have_sym = false;
     if (__any_sync(0xffffffffu, fire)) {
-      // ---------------- TED instant: matched filters (A4), every tap address wrapped into the 64-slot ring ----------------
       float2 am = make_float2(0.0f, 0.0f), as = make_float2(0.0f, 0.0f);
       const uint32_t e = ((pos - 1u) << 7) & 0x1f80u;
 #pragma unroll
-      for (int i = 0; i < FAST_NTAPS; ++i) {
+      for (int i = 0; i < FAST_NTAPS; ++i) {    // filter.rs:363-377 with packed exact f32 ops, see mf_soft
         const float v = lds_f32(y_lane + ((e - (uint32_t)(i << 7)) & 0x1f80u));
         const float4 t = tapsm[i];
         const float2 vv = make_float2(v, v);
-        am = __ffma2_rn(am, one2, __ffma2_rn(vv, make_float2(t.x, t.y), negz2));     // filter.rs:363-377, see mf_soft
+        am = __ffma2_rn(am, one2, __ffma2_rn(vv, make_float2(t.x, t.y), negz2));
         as = __ffma2_rn(as, one2, __ffma2_rn(vv, make_float2(t.z, t.w), negz2));
       }
       const float soft = rclamp(FSUB(hypot_fixed(am.x, am.y), hypot_fixed(as.x, as.y)), -1.0f, 1.0f);  // demod.rs:163
@@ -785,11 +808,42 @@ __global__ void __maxnreg__(DN_MAXREG) same_rx_dense_kernel(const __grid_constan
         pend = 0u;
       }
     }
+    // ---------------- the lock flag flipped: the look-ahead samples pos .. rp-1 were speculated with the old flag ----------------
+    const bool flipped = (a.flags & FLAG_AGC_LOCKED) != lock_before;
+    if (__any_sync(0xffffffffu, flipped)) {
+      if (flipped) {
+        const uint32_t base = rp - nlast;                  // first sample of the last chunk
+        const uint32_t idx = pos - base;                   // samples of it that are final (pos >= base: look-ahead < 8)
+        const uint32_t newbits = (a.flags & FLAG_AGC_LOCKED) ? 0xffu : 0u;
+        lockmask = (lockmask & ((1u << idx) - 1u)) | (newbits & ~((1u << idx) - 1u));
+        const uint32_t ys = y_lane + ((base & (FAST_RING - 1)) << 7);
+        float gr = g0;
+#pragma unroll
+        for (int i = 0; i < LA_CHUNK; ++i) {
+          if (i < (int)nlast) {
+            const float y = agc_step(gr, dlast[i], ((lockmask >> i) & 1u) ? 0.0f : bw, gmin, gmax);
+            if (i >= (int)idx) sts_f32(ys + (uint32_t)(i << 7), y);
+          }
+        }
+        g = gr;
+      }
+      __syncwarp();
+    }
   }
 
   if (!valid || len == 0u) return;
+
+  // ---- store state (same f32 layout as the generic kernel); pos == rp == len: g is the gain at the sample counter ----
+  a.g = g;
   lane_store(a, p, st, a.n0 + len);
-  if (!dc_windows_stored) dc_store(dc, DcToState{st, L});
+  LANE_ST(st, L, F_DC_FFSUM) = __float_as_uint((float)S1);
+  LANE_ST(st, L, F_DC_FBSUM) = __float_as_uint((float)S2 * 0.0625f);
+  if (!dc_windows_stored) {
+#pragma unroll
+    for (int i = 0; i < FAST_DCL; ++i) LANE_ST(st, L, L.dc_ff + i) = __float_as_uint((float)s16_at(rawh, i));
+  }
+  for (int i = 0; i < FAST_DCL; ++i)
+    LANE_ST(st, L, L.dc_fb + i) = __float_as_uint((float)s1ring[((len + i) & (FAST_DCL - 1)) * 32 + lane] * 0.0625f);
   for (int i = 0; i < FAST_NTAPS; ++i)
     LANE_ST(st, L, L.win + i) = __float_as_uint(yring[((int)(len + i - FAST_NTAPS) & (FAST_RING - 1)) * 32 + lane]);
 }
@@ -930,7 +984,8 @@ __device__ __forceinline__ void ws_producer(const SameParams& p, uint32_t* st, c
   if (valid && len != 0u && !dc_windows_stored) dc_store(dc, DcToState{st, L});
 }
 
-__global__ void __launch_bounds__(WS_THREADS) same_rx_ws_kernel(const __grid_constant__ SameParams p,
+// up to four blocks per SM (engine policy): 12 warps = three per sub-partition -> at most 168 registers
+__global__ void __launch_bounds__(WS_THREADS, 4) same_rx_ws_kernel(const __grid_constant__ SameParams p,
                                                         const __grid_constant__ SameTaps2 taps,
                                                         const int16_t* __restrict__ samples,
                                                         const unsigned long long* __restrict__ offsets,
@@ -1061,7 +1116,7 @@ __global__ void __launch_bounds__(WS_THREADS) same_rx_ws_kernel(const __grid_con
     const int k0 = use_pre ? WS_SPEC : 0;
     const uint32_t od = (((pos + (uint32_t)k0) << 7) & 0x3f80u) | ((uint32_t)lane << 2);   // d ring: 128 slots
     const uint32_t oy = (((pos + (uint32_t)k0) << 7) & 0x1f80u) | ((uint32_t)lane << 2);   // y ring: 64 slots + mirror
-    g = agc_segment<0x3fffu, true>(g, bw_eff, gmin, gmax, d_base, y_base, od, oy, k0, nmin, maxseg, nseg);
+    g = agc_segment<0x3fffu>(g, bw_eff, gmin, gmax, d_base, y_base, od, oy, k0, nmin, maxseg, nseg);
     if (nseg > 0) a.g = g;
     pre_ok = false;
     pos += (uint32_t)nseg;
@@ -1078,7 +1133,7 @@ __global__ void __launch_bounds__(WS_THREADS) same_rx_ws_kernel(const __grid_con
     bool have_sym = false;
     if (__any_sync(0xffffffffu, fire)) {
       // ---------------- TED instant: matched filters (A4, packed exact f32 ops), timing loop (A5) ----------------
-      const float soft = mf_soft<true>(yring, tapsm, lane, pos, one2, negz2);
+      const float soft = mf_soft(yring, tapsm, lane, pos, one2, negz2);
       if (fire) {
         const float rem = FSUB(a.until, (float)a.clock);  // receiver.rs:352
         a.clock = 0;
@@ -1448,11 +1503,11 @@ __global__ void same_evsort_scatter(const same_event* __restrict__ ev, uint32_t 
 // Launchers (called from same_engine.cu)
 // ----------------------------------------------------------------------------------------------------------------
 // kernel ids: 1 generic, 2 single-warp fast, 3 pipelined four-warp, 4 three-warp, 5 single-warp fast fed by the front-end
-// kernel's tiles (split pipeline), 6 dense single-warp (14 resident blocks per SM).  `fast_variant`: 0 = y ring with mirror slots, 1 = without (more resident warps).
+// kernel's tiles (split pipeline), 6 look-ahead single-warp (16 resident warps per SM).
 extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps, const SameTaps2* taps2, int force_generic,
                                       uint32_t lanes_per_warp, const void* d_samples_v, int sample_fmt,
                                       const unsigned long long* d_offsets, const uint32_t* d_lengths,
-                                      const SameTiles* tiles, int fast_variant, cudaStream_t stream) {
+                                      const SameTiles* tiles, cudaStream_t stream) {
   const uint32_t blocks = (p->n_streams + 31u) / 32u;
   const int16_t* d_samples = static_cast<const int16_t*>(d_samples_v);
   // The fast kernels need the 22050 Hz geometry (42 taps, DC length 16) and s16 samples (their DC blocker is an
@@ -1466,17 +1521,11 @@ extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps,
       t = *tiles;
       const dim3 grid((t.n_max + FE_RUN * FE_WARPS - 1u) / (FE_RUN * FE_WARPS), blocks);
       same_dev::same_frontend_kernel<<<grid, FE_WARPS * 32, 0, stream>>>(*p, d_samples, d_offsets, d_lengths, t);
-      if (fast_variant == 1)
-        same_dev::same_rx_fast_kernel<true, false, 12><<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes, t);
-      else
-        same_dev::same_rx_fast_kernel<true, true, 1><<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes, t);
+      same_dev::same_rx_fast_kernel<true><<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes, t);
     } else if (force_generic == 6) {
-      same_dev::same_rx_dense_kernel<<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes);
+      same_dev::same_rx_la_kernel<<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes);
     } else if (force_generic == 2) {
-      if (fast_variant == 1)
-        same_dev::same_rx_fast_kernel<false, false, 12><<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes, t);
-      else
-        same_dev::same_rx_fast_kernel<false, true, 1><<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes, t);
+      same_dev::same_rx_fast_kernel<false><<<fblocks, 32, 0, stream>>>(*p, *taps2, d_samples, d_offsets, d_lengths, lanes, t);
     } else if (force_generic == 3) {
       // per device, cheap: set on every launch rather than tracking which devices have seen it
       cudaError_t e = cudaFuncSetAttribute(same_dev::same_rx_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

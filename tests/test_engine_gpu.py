@@ -237,8 +237,7 @@ def test_fast_and_generic_kernels_agree():
     got = [[] for _ in recs]
     k = 0
     while any(p < len(r) for p, r in zip(pos, recs)):
-        rx.set_option("kernel", 1 + k % 6)   # 1 generic, 2 single-warp fast, 3 pipelined, 4 three-warp, 5 split (front end + tile-fed), 6 dense
-        rx.set_option("fast_variant", (k // 6) % 2)   # single-warp kernel's window ring with / without mirror slots
+        rx.set_option("kernel", 1 + k % 6)   # 1 generic, 2 single-warp fast, 3 pipelined, 4 three-warp, 5 split (front end + tile-fed), 6 look-ahead
         k += 1
         chunks = []
         for s_ in range(len(recs)):
@@ -254,7 +253,7 @@ def test_fast_and_generic_kernels_agree():
         assert_events_equal(want[s_], o.events(), f"stream {s_} generic kernel vs oracle")
 
 
-@pytest.mark.parametrize("kernel", [2, 3, 4, 5, 6, 12, 15])
+@pytest.mark.parametrize("kernel", [2, 3, 4, 5, 6])
 def test_each_fast_kernel_matches_oracle(kernel):
     """Every fast-kernel flavour on its own, whole streams in one submit and in 3 s chunks: golden recordings and
     synthetic streams with bursts against the oracle, event for event."""
@@ -268,14 +267,12 @@ def test_each_fast_kernel_matches_oracle(kernel):
         o.process_s16(r)
         want.append(o.events())
     rx = b.build_batch(len(recs))
-    rx.set_option("kernel", kernel % 10)          # 1x = the same kernel with fast_variant 1 (no mirror slots)
-    rx.set_option("fast_variant", kernel // 10)
+    rx.set_option("kernel", kernel)
     got = rx.process(recs)
     for s_ in range(len(recs)):
         assert_events_equal(got[s_], want[s_], f"kernel {kernel} stream {s_} one submit")
     rx = b.build_batch(len(recs))
-    rx.set_option("kernel", kernel % 10)
-    rx.set_option("fast_variant", kernel // 10)
+    rx.set_option("kernel", kernel)
     got = [[] for _ in recs]
     step = 3 * 22050 + 7
     for lo in range(0, max(len(r) for r in recs), step):
@@ -356,7 +353,7 @@ def test_config3_full_size_every_stream_vs_oracle():
     """BASELINE config 3 at full size (4096 streams x 60 s, 10.8 GB of samples), BASELINE.md §3 row 3: the engine's
     events on EVERY stream are bit-identical to the CPU oracle's (kind, sample counter, symbol count, bytes, parity /
     voting counts); the engine's kernel for this batch size (pipelined) run three times, and every other kernel once
-    (generic, single-warp with and without mirror slots, dense single-warp, three-warp, split front end + tile-fed), produce the same
+    (generic, single-warp, look-ahead single-warp, three-warp, split front end + tile-fed), produce the same
     event stream; every stream decodes its planned header."""
     _torch()
     ns, secs = 4096, 60.0
@@ -370,10 +367,9 @@ def test_config3_full_size_every_stream_vs_oracle():
     want = _canonical_raw(oe, op)
     del host
     ref = None
-    for kernel in (0, 0, 0, 1, 2, 4, 5, 6, 12):
+    for kernel in (0, 0, 0, 1, 2, 4, 5, 6):
         rx = b.build_batch(ns)
-        rx.set_option("kernel", kernel % 10)
-        rx.set_option("fast_variant", kernel // 10)
+        rx.set_option("kernel", kernel)
         rx.submit_device(buf.data_ptr(), ns * stride, offsets, lengths)
         rx.sync()
         evs, pay = _canonical_raw(*rx.drain_raw())

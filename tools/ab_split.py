@@ -41,13 +41,12 @@ def main():
         rx = sb.SameReceiverBuilder.samedec(RATE).build_batch(ns)
         out = {"streams": ns, "seconds": secs, "samples": ns * n, "policy_kernel": rx.get_option("kernel_selected")}
         ref = None
-        cases = [("fused_single_warp", 2, 0), ("fused_dense", 6, 0), ("fused_three_warp", 4, 0), ("fused_pipelined", 3, 0),
+        cases = [("fused_single_warp", 2, 0), ("fused_lookahead", 6, 0), ("fused_three_warp", 4, 0), ("fused_pipelined", 3, 0),
                  ("split_frontend_plus_tilefed", 5, 0)]
         if "--quick" in sys.argv:
             cases = cases[:2]
         for name, kernel, variant in cases:
             rx.set_option("kernel", kernel)
-            rx.set_option("fast_variant", variant)
             best = None
             for r in range(reps + 1):
                 rx.reset()

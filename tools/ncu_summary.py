@@ -2,6 +2,7 @@
 """Write a text summary of an ncu report (the numbers DESIGN.md / bench.py cite) — run here, no GPU needed.
 
 usage: tools/ncu_summary.py REPORT.ncu-rep WARPS SAMPLES_PER_STREAM OUT.txt [--traffic-json OUT.json STREAMS SECONDS]
+                            [--kernel REGEX] [--skip N]     (pick one launch of a multi-kernel report)
 """
 import csv
 import io
@@ -25,7 +26,13 @@ METRICS = [
 
 def main():
     rep, warps, samples, out = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    sel = []
+    if "--kernel" in sys.argv:
+        sel += ["--kernel-name", "regex:" + sys.argv[sys.argv.index("--kernel") + 1]]
+    if "--skip" in sys.argv:
+        sel += ["--launch-skip", sys.argv[sys.argv.index("--skip") + 1]]
+    sel += ["--launch-count", "1"]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + sel, capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, vals = rows[0], rows[1], rows[2]
     got = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
@@ -33,14 +40,15 @@ def main():
     for m in METRICS:
         if m in got:
             lines.append(f"{m:75s} {got[m][0]:>18s} {got[m][1]}")
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
     srows = list(csv.reader(io.StringIO(src)))
     h = srows[1]
     ie, ss = h.index("Instructions Executed"), h.index("# Samples")
     stall_cols = {n: h.index(n) for n in h if n.startswith("stall_") and "Not Issued" not in n}
     data = [r for r in srows[2:] if len(r) > ie and r[ie].isdigit()]
     tot = sum(int(r[ie]) for r in data)
-    lines += ["", f"executed warp-instructions {tot:,} = {tot / (warps * samples):.1f} per sample step ({warps} warps x {samples} samples)"]
+    raw_inst = float(got["smsp__inst_executed.sum"][0].replace(",", "")) if "smsp__inst_executed.sum" in got else float(tot)
+    lines += ["", f"executed warp-instructions {raw_inst:,.0f} = {raw_inst / (warps * samples):.1f} per sample step ({warps} warps x {samples} samples)"]
     agg = {}
     for r in data:
         for n, c in stall_cols.items():
@@ -65,7 +73,16 @@ def main():
             f = float(v.replace(",", ""))
             return f * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
 
-        json.dump({"streams": streams, "seconds": seconds, "report": rep,
+        import datetime
+        import hashlib
+        import os
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        hh = hashlib.sha256()
+        for f in ("same_kernels.cu", "same_lane.cuh", "same_transport.cuh", "same_params.h"):
+            hh.update(open(os.path.join(root, "sameold_b200", "csrc", f), "rb").read())
+        json.dump({"streams": streams, "seconds": seconds, "report": os.path.basename(rep),
+                   "captured": datetime.date.today().isoformat(), "kernel_src_sha16": hh.hexdigest()[:16],
+                   "kernel": got.get("Kernel Name", ("?", ""))[0].split("(")[0],
                    "dram_bytes_per_launch": int(num("dram__bytes_read.sum") + num("dram__bytes_write.sum")),
                    "dram_bytes_read": int(num("dram__bytes_read.sum")), "dram_bytes_write": int(num("dram__bytes_write.sum"))},
                   open(jout, "w"), indent=1)
