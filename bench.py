@@ -309,7 +309,8 @@ def main():
         rx.set_option("kernel", args.kernel)
     if args.lanes_per_warp:
         rx.set_option("lanes_per_warp", args.lanes_per_warp)
-    kernel_names = {1: "same_rx_generic_kernel", 2: "same_rx_fast_kernel", 3: "same_rx_pipe_kernel", 4: "same_rx_ws_kernel"}
+    kernel_names = {1: "same_rx_generic_kernel", 2: "same_rx_fast_kernel", 3: "same_rx_pipe_kernel", 4: "same_rx_ws_kernel",
+                    5: "same_frontend_kernel + same_rx_fast_kernel<tile-fed>", 6: "same_rx_la_kernel"}
     kernel_name = kernel_names.get(rx.get_option("kernel_selected"), "same_rx_kernel")
     audio_per_step = ns * n_samples / RATE
 

@@ -205,7 +205,8 @@ int same_engine_read_soft_trace(same_engine* e, uint32_t stream, same_soft_symbo
  * Implies sync. */
 int same_engine_set_option(same_engine* e, const char* key, int value);
 /* Reads an option back; additionally "kernel_selected": the kernel the next s16 submit will launch (1 generic,
- * 2 single-warp, 3 pipelined, 4 three-warp) — the policy result for this batch size unless "kernel" overrides it. */
+ * 2 single-warp, 3 pipelined, 4 three-warp, 6 look-ahead single-warp) — the policy result for this batch size unless
+ * "kernel" overrides it. */
 int same_engine_get_option(same_engine* e, const char* key, int* value);
 
 /* Measurement aid: runs only the front-end kernel (feed-forward stages: s16 -> f32, DC blocker; 2 B read + 4 B written

@@ -37,6 +37,18 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS if os.path.exists(os.path.join(CSRC, f)))
 
 
+def build_variant(name, defines):
+    """Diagnostic: an extra in-tree build of the same ABI with -D switches (A/B timing via SAME_B200_LIB, tools/ab.sh)."""
+    os.makedirs(OUT_DIR, exist_ok=True)
+    out = os.path.join(OUT_DIR, name)
+    srcs = [os.path.join(CSRC, f) for f in SOURCES]
+    cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")] + ["-D" + d for d in defines] + ["-shared", "-o", out] + srcs
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + (r.stdout + r.stderr)[-4000:])
+    return out
+
+
 def build_native(force=False, verbose=False):
     """Compile every CUDA source for sm_100a into one shared library.  Returns the library path."""
     if not force and not needs_build():

@@ -84,7 +84,7 @@ struct same_engine {
   int force_generic = 0;
   uint32_t lanes_per_warp = 32;   // streams per warp in the fast kernel (lane-sparse warps for small batches)
   int sm_count = 148;
-  int kernel_auto = 0;            // fast-kernel flavour when force_generic == 0: 3 pipelined, 4 three-warp, 2 single-warp
+  int kernel_auto = 0;            // fast-kernel flavour when force_generic == 0: 3 pipelined, 4 three-warp, 2 single-warp, 6 look-ahead
   SameTiles tiles{nullptr, nullptr, 0u};   // split pipeline (kernel 5): front-end output, allocated on first use
   size_t tiles_cap = 0;           // floats
   bool saw_f32 = false;           // an f32 submit happened since create / reset(all): DC state may be non-integer -> generic kernel
@@ -439,15 +439,17 @@ int same_engine_create(const same_config* cfg_in, int device, uint32_t n_streams
   }
   p.f_one = 1.0f; p.f_negzero = -0.0f;
   {
-    // Kernel / mapping policy for the 22050 Hz class (measured on B200, profiles/README.md):
-    //  * up to 1 block per SM: four-warp pipelined kernel (producer / AGC / space filter / consumer), every warp on
-    //    its own scheduler: the per-stream dependent chain is what bounds the run time, so it is cut into stages.
-    //  * up to 4 blocks per SM: three-warp kernel (producer / look-ahead AGC / consumer): fewer instructions in total,
-    //    still latency-hiding across the co-resident blocks.
-    //  * larger batches: single-warp fast kernel, 32 streams per warp (issue-bound regime: the fewest instructions win
-    //    and helper warps would only compete for issue slots).
-    //  Measured on B200 (20 s streams, ms per launch, pipelined / three-warp / single-warp): 4096 streams 24.0 / 24.9 /
-    //  41.6; 8192: 36.8 / 29.1 / 42.4; 16384: 74.6 / 40.0 / 43.3; 65536: 228 / 158 / 116  (tools/matrix.sh).
+    // Kernel / mapping policy for the 22050 Hz class (measured on B200, tables in profiles/README.md), by 32-stream
+    // blocks per SM:
+    //  * <= 1: four-warp pipelined kernel (producer / AGC / space filter / consumer), every warp on its own scheduler:
+    //    the per-stream dependent chain is what bounds the run time, so it is cut into stages.
+    //  * <= 4: three-warp kernel (producer / look-ahead AGC / consumer): fewer instructions in total, still
+    //    latency-hiding across the co-resident blocks.
+    //  * <= 8: single-warp fast kernel (8 resident blocks per SM: the whole batch is one wave; fewest instructions).
+    //  * more: single-warp look-ahead kernel (16 resident warps per SM, no d ring): the issue-bound regime.
+    //  20 s streams, ms per launch, pipelined / three-warp / single-warp / look-ahead: 4096 streams 24.0 / 24.9 / 41.6 / -;
+    //  8192: 36.8 / 29.1 / 43.3 / 66; 16384: 74.6 / 40.0 / 43.9 / 70; 32768: - / - / 57.7 / 81; 49152: - / - / 109 / 83;
+    //  65536: 228 / 158 / 116 / 97.
     // Option "lanes_per_warp" spreads streams over more, lane-sparse warps (diagnostic).  No environment variable is
     // read here: same_engine_set_option is the only override.
     int sms = 148;
@@ -455,7 +457,7 @@ int same_engine_create(const same_config* cfg_in, int device, uint32_t n_streams
     e->sm_count = sms;
     e->lanes_per_warp = 32;
     const uint32_t blocks32 = (n_streams + 31u) / 32u;
-    e->kernel_auto = (blocks32 <= (uint32_t)sms) ? 3 : (blocks32 <= 4u * (uint32_t)sms) ? 4 : 2;
+    e->kernel_auto = (blocks32 <= (uint32_t)sms) ? 3 : (blocks32 <= 4u * (uint32_t)sms) ? 4 : (blocks32 <= 8u * (uint32_t)sms) ? 2 : 6;
   }
   p.spt = sps / 2.0f;                                                         // symsync.rs:146
   {

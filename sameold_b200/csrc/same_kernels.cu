@@ -615,16 +615,22 @@ __global__ void __launch_bounds__(32, 8) same_rx_fast_kernel(const __grid_consta
 //     (agc.rs:74), so DC blocker and AGC run together in static 8-sample chunks (one 16-byte load), straight from
 //     registers into the y ring, until they have passed the lane's next TED instant — at most 7 samples of look-ahead.
 //     The look-ahead is exact speculation: if the symbol stages at that instant flip the lock flag, the tail of the last
-//     chunk is recomputed from its saved inputs (d values, starting gain, per-sample flag mask).  No d ring, no
-//     per-sample loop of run-time length, and the independent DC arithmetic of later samples fills the issue slots
-//     under the gain chain.
+//     chunk is recomputed from its saved inputs (8 d values in registers, starting gain, per-sample flag mask).  No d
+//     ring, no per-sample loop of run-time length, and the independent DC arithmetic of later samples fills the issue
+//     slots under the gain chain.  Each lane streams along its own row, so the 128-byte line two ahead is pulled into
+//     L2 with a prefetch (without it the first load of every line is the kernel's top stall).
 //   * DC-blocker history: the last 16 raw samples stay in registers (packed pairs), the last 16 values of S1 live in a
 //     2 KB shared-memory ring (static offsets from a per-chunk base).
 //   * y ring: 64 slots, no mirror (8 KB): the matched filter wraps every tap address into the ring.
 // Same arithmetic, same rounds, same parking rules and same resident state as the other fast kernels.
+// Measured (profiles/README.md, round 2): 65 536 x 20 s 97 ms against 116 ms; 49 152: 83 / 109; 131 072 x 10 s: 88 / 101;
+// below 8 blocks per SM the fast kernel's fewer instructions win (32 768: 58 / 81).  Tried and dropped: cold lane
+// state through the state words around each symbol stage (131 ms), redo inputs in shared memory (108), byte path as a
+// real call (115), 168 registers / 12 warps per SM (142: the 13.8 warps per SM of 65 536 streams then leave a tail wave).
 // ----------------------------------------------------------------------------------------------------------------
 #define LA_CHUNK 8
 #define LA_MAXREG 128
+constexpr int LA_MF_UNROLL_N = 14;   // matched-filter unroll: 3 x 14 taps (the full unroll costs registers the loop cannot spare)
 
 __global__ void __maxnreg__(LA_MAXREG) same_rx_la_kernel(const __grid_constant__ SameParams p,
                                                          const __grid_constant__ SameTaps2 taps,
@@ -723,6 +729,8 @@ __global__ void __maxnreg__(LA_MAXREG) same_rx_la_kernel(const __grid_constant__
           }
           pf_ok = src != nullptr && aligned && (len - rp) >= 2u * LA_CHUNK;
           if (pf_ok) nx = __ldg(reinterpret_cast<const int4*>(src + rp + LA_CHUNK));
+          // each lane streams along its own row: pull the 128-byte line two ahead (64 samples each) into L2 early
+          if (pf_ok && (rp & 63u) == 0u && (len - rp) > 192u) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + rp + 128));
 #pragma unroll
           for (int i = 0; i < LA_CHUNK; ++i) {
             const int x = s16_at(cur, i), x16 = s16_at(rawh, i), x15 = s16_at(rawh, i + 1);
@@ -783,10 +791,11 @@ __global__ void __maxnreg__(LA_MAXREG) same_rx_la_kernel(const __grid_constant__
     bool have_sym = false;
     if (__any_sync(0xffffffffu, fire)) {
       float2 am = make_float2(0.0f, 0.0f), as = make_float2(0.0f, 0.0f);
-      const uint32_t e = ((pos - 1u) << 7) & 0x1f80u;
-#pragma unroll
+      uint32_t e = (pos - 1u) << 7;             // running byte offset of the tap's sample, wrapped into the ring per tap
+#pragma unroll LA_MF_UNROLL_N
       for (int i = 0; i < FAST_NTAPS; ++i) {    // filter.rs:363-377 with packed exact f32 ops, see mf_soft
-        const float v = lds_f32(y_lane + ((e - (uint32_t)(i << 7)) & 0x1f80u));
+        const float v = lds_f32(y_lane + (e & 0x1f80u));
+        e -= 128u;
         const float4 t = tapsm[i];
         const float2 vv = make_float2(v, v);
         am = __ffma2_rn(am, one2, __ffma2_rn(vv, make_float2(t.x, t.y), negz2));
@@ -801,7 +810,9 @@ __global__ void __maxnreg__(LA_MAXREG) same_rx_la_kernel(const __grid_constant__
       }
     }
     // ---------------- symbol: squelch now (A6), byte path (A7-A9) on the aligned rounds ----------------
-    if (have_sym) pend = symbol_squelch(a, p, s, st, blob, a.ted1, a.ted2, a.n0 + pos);
+    if (have_sym) {
+      pend = symbol_squelch(a, p, s, st, blob, a.ted1, a.ted2, a.n0 + pos);
+    }
     if (byte_round && __any_sync(0xffffffffu, pend != 0u)) {
       if (pend != 0u) {
         symbol_byte(a, p, s, st, blob, (pend & SYM_ADJUSTED) != 0u, a.n0 + pos);
@@ -821,7 +832,8 @@ __global__ void __maxnreg__(LA_MAXREG) same_rx_la_kernel(const __grid_constant__
 #pragma unroll
         for (int i = 0; i < LA_CHUNK; ++i) {
           if (i < (int)nlast) {
-            const float y = agc_step(gr, dlast[i], ((lockmask >> i) & 1u) ? 0.0f : bw, gmin, gmax);
+            const float din = dlast[i];
+            const float y = agc_step(gr, din, ((lockmask >> i) & 1u) ? 0.0f : bw, gmin, gmax);
             if (i >= (int)idx) sts_f32(ys + (uint32_t)(i << 7), y);
           }
         }
