@@ -215,6 +215,19 @@ def bind_host_cpus(device, local_rank, local_world):
         return {"how": "unbound", "node": None, "cpus": len(allowed)}
 
 
+def device_for_rank(local_rank, local_world, n_devices):
+    """Which GPU a rank drives when the box has more GPUs than the job has ranks: the ranks are striped over the device
+    index range (8 GPUs: 0, 4, 1, 5, 2, 6, 3, 7) instead of packed into the first N.  Measured on this pod's 8-GPU
+    boxes (profiles/README.md, round 2): GPUs 0-3 share one host path that sustains ~115 GB/s of pinned host->device
+    copies in total (29 GB/s each when all four copy, 55 GB/s each for any two), GPUs 4-7 another; `nvidia-smi topo`
+    and sysfs expose nothing (one NUMA node), so the order is a static spread, not a lookup."""
+    if local_world <= 1 or n_devices <= local_world:
+        return local_rank
+    half = n_devices // 2
+    order = [i // 2 + (i % 2) * half for i in range(2 * half)] + list(range(2 * half, n_devices))
+    return order[local_rank]
+
+
 def kernel_source_sha16():
     """Hash of the receiver-kernel sources: ties profiles/rx_kernel_traffic.json (an ncu capture) to the code it was
     taken from, so a stale capture is dropped instead of silently reported."""
@@ -261,11 +274,14 @@ def main():
     import sameold_b200 as sb
     from sameold_b200 import synth, _lib
 
-    torch.cuda.set_device(local_rank)
-    binding = bind_host_cpus(local_rank, local_rank, local_world) if world > 1 else {"how": "single rank: unbound", "node": None,
-                                                                                      "cpus": len(os.sched_getaffinity(0))}
+    all_cores = os.sched_getaffinity(0)
+    device = device_for_rank(local_rank, local_world, torch.cuda.device_count())
+    torch.cuda.set_device(device)
+    binding = bind_host_cpus(device, local_rank, local_world) if world > 1 else {"how": "single rank: unbound", "node": None,
+                                                                                  "cpus": len(all_cores)}
+    binding["rank_to_device"] = [device_for_rank(r, local_world, torch.cuda.device_count()) for r in range(local_world)]
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device))
 
     def barrier():
         if world > 1:
@@ -286,7 +302,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    comm = {"world": world, "rank": rank, "local_rank": local_rank, "barrier": barrier, "max": max_over_ranks,
+    comm = {"world": world, "rank": rank, "local_rank": device, "barrier": barrier, "max": max_over_ranks,
             "sum": sum_over_ranks}
     if args.config == 5:
         return run_config5(args, comm)
@@ -299,12 +315,12 @@ def main():
     if args.no_bursts:
         for pl in plans:
             pl.burst_starts, pl.burst_payloads = [], []
-    synth.generate_on_device(plans, buf.data_ptr(), stride, n_samples, RATE, device=local_rank)
+    synth.generate_on_device(plans, buf.data_ptr(), stride, n_samples, RATE, device=device)
     offsets = np.arange(ns, dtype=np.uint64) * np.uint64(stride)
     lengths = np.full(ns, n_samples, np.uint32)
 
     builder = sb.SameReceiverBuilder.samedec(RATE)
-    rx = builder.build_batch(ns, device=local_rank)
+    rx = builder.build_batch(ns, device=device)
     if args.kernel:
         rx.set_option("kernel", args.kernel)
     if args.lanes_per_warp:
@@ -326,7 +342,7 @@ def main():
     n_headers = int((evs["kind"] == 18).sum())
     n_events = int(evs.size)
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(device)
     launches0 = rx.launch_count()
     kernel_ms = []
     barrier()
@@ -404,7 +420,7 @@ def main():
         ms = C.c_float()
         barrier()
         width = (bounds[1] - bounds[0]) * 2
-        rc = lib.same_h2d_probe(local_rank, C.c_void_p(hptr), stride * 2, width, ns, nchunk, C.byref(ms))
+        rc = lib.same_h2d_probe(device, C.c_void_p(hptr), stride * 2, width, ns, nchunk, C.byref(ms))
         barrier()
         probe_ms = max_over_ranks(ms.value if rc == 0 else float("nan"))
         ceiling_gbs = world * ns * width * nchunk / (probe_ms * 1e-3) / 1e9
@@ -425,8 +441,11 @@ def main():
         if rank == 0:
             k = min(args.cpu_sample_streams, ns)
             sample = buf[:k, :n_samples].cpu().numpy()
-            cores = len(os.sched_getaffinity(0)) if world > 1 else (os.cpu_count() or 1)
+            mine = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, all_cores)        # the baseline gets every host core (the other ranks wait at the barrier)
+            cores = len(all_cores)
             v, secs, nb, nm = cpu_baseline(sample, builder.config(), cores)
+            os.sched_setaffinity(0, mine)
             cpu = {"value": round(v, 1), "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"first {k} streams x {args.seconds:g} s of this workload, one receiver per stream, {cores} threads, best of 2 ({secs:.2f} s)",
                    "what": "oracle/ C++ restatement of sameold 0.6.0 (link + transport layers), g++ -O2 -ffp-contract=off; the Rust crate cannot be built here"}
