@@ -865,14 +865,14 @@ __global__ void __maxnreg__(LA_MAXREG) same_rx_la_kernel(const __grid_constant__
 // tiles  d[(tile * n_max + n) * 32 + lane],  tile = 32 consecutive streams — one 128-byte line per (tile, sample), the
 // layout a warp of the loop kernel reads with one coalesced request.  HBM-bound: 2 B read + 4 B written per sample.
 //
-// One warp = one tile x one run of FE_RUN samples; lane = stream.  The DC blocker has finite memory (31 samples), so a
+// One warp = one tile x one run of FE_RUN (2048) samples; lane = stream.  The DC blocker has finite memory (31 samples), so a
 // run that does not start the chunk warms up on the 32 samples before it (integer recursion from zero is exact after
 // 31 samples) and is independent of every other run; the first run of a stream starts from the resident state.  Reads:
 // each lane streams along its own row with 16-byte loads (L1 keeps the 128-byte lines between a lane's consecutive
 // loads); writes: 32 lanes x 4 B = one full line per sample.  The run that ends a stream's chunk writes the new DC
 // state to tiles.dc_next (committed to the state words by the tile-fed loop kernel).
 // ----------------------------------------------------------------------------------------------------------------
-#define FE_RUN 512
+#define FE_RUN 2048      // samples per run: 32 of warm-up per run = 1.6 % extra reads (512: 83.9 %, 2048: 87.4 % of HBM peak)
 #define FE_WARPS 4
 __global__ void __launch_bounds__(FE_WARPS * 32) same_frontend_kernel(const __grid_constant__ SameParams p,
                                                                       const int16_t* __restrict__ samples,
@@ -1205,18 +1205,20 @@ __global__ void __launch_bounds__(WS_THREADS, 4) same_rx_ws_kernel(const __grid_
 // |matched filter output| over the 42 samples that end at sample index `end` (exclusive); taps from the constant bank.
 // One rounded multiply and one rounded add per component and tap, newest sample first (demod.rs:156-163).
 __device__ __forceinline__ float pk_mag(const float* yring, const float2* __restrict__ h, const int lane,
-                                        const uint32_t end) {
+                                        const uint32_t end, const float f_one, const float f_negzero) {
   int nslot = (int)((end - 1u) & (PK_YRING - 1));
   if (nslot < FAST_NTAPS - 1) nslot += PK_YRING;
   const float* yp = yring + nslot * 32 + lane;
-  float re = 0.0f, im = 0.0f;
+  // packed exact f32 ops (see mf_soft): 3 instructions per tap instead of 5; measured 60.9 against 62.3 ms on config 3
+  // although the dependent FFMA2 chain is slower per step than FADD (6 against 4 cycles) -- the warp was issue-bound
+  const float2 one2 = make_float2(f_one, f_one), negz2 = make_float2(f_negzero, f_negzero);
+  float2 acc = make_float2(0.0f, 0.0f);
 #pragma unroll
   for (int i = 0; i < FAST_NTAPS; ++i) {
     const float v = yp[-i * 32];
-    re = FADD(re, FMUL(v, h[i].x));
-    im = FADD(im, FMUL(v, h[i].y));
+    acc = __ffma2_rn(acc, one2, __ffma2_rn(make_float2(v, v), h[i], negz2));
   }
-  return hypot_fixed(re, im);
+  return hypot_fixed(acc.x, acc.y);
 }
 
 // one block per SM at most (engine policy): every register the role code wants
@@ -1335,7 +1337,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) same_rx_pipe_kernel(const __gri
     while (true) {
       ws_bar_sync(PK_BAR_POS, 96);
       if (sh_done) break;
-      sh_space[lane] = pk_mag(yring, taps.space, lane, sh_pos[lane]);
+      sh_space[lane] = pk_mag(yring, taps.space, lane, sh_pos[lane], p.f_one, p.f_negzero);
       __threadfence_block();
       ws_bar_arrive(PK_BAR_SPACE, 64);
     }
@@ -1412,7 +1414,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) same_rx_pipe_kernel(const __gri
     const float off = rclamp(rem, -0.5f, 0.5f);                              // symsync.rs:220
     const float offq = __fdiv_rn(off, p.spt);                                // symsync.rs:225
     asm volatile("" ::"f"(offq));
-    const float mag_m = pk_mag(yring, taps.mark, lane, pos);
+    const float mag_m = pk_mag(yring, taps.mark, lane, pos, p.f_one, p.f_negzero);
     asm volatile("" ::"f"(mag_m));          // keep the mark magnitude ahead of the wait for the space magnitude
     ws_bar_sync(PK_BAR_SPACE, 64);
     bool have_sym = false;

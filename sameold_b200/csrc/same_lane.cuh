@@ -41,18 +41,26 @@ __device__ __forceinline__ bool fires(float until, float cf) {
   const float r = FSUB(until, cf);
   return r <= 0.0f || fabsf(r) < 0.5f;
 }
-// Smallest c > clock_now that fires.  The predicate is monotone in c, so the closed form floor(until-0.5)+1 is
-// verified against the reference predicate and corrected if a rounding corner case ever disagrees.  Integer<->float
-// conversions use the 2^23 magic-number form (FMA/ALU pipes) instead of the conversion unit.
+// Smallest c > clock_now that fires.  The predicate is monotone in c.
+// Closed form for 1 <= until < 2^22 (every realistic rate: until is about half a symbol, 21 samples at 22050 Hz):
+//   c* = floor(until - 0.5) + 1.
+// Proof that this is the reference's first firing clock: until - 0.5 is exact (0.5 is a multiple of ulp(until) <= 0.25
+// and the result lies in a binade at or below until's); for an integer 1 <= c <= 2^22 the real difference
+// d = until - c is a multiple of ulp(until) with |d| <= until, hence representable, so FSUB(until, c) == d exactly.
+// For c <= floor(until - 0.5): d >= 0.5, no fire.  For c = c*: -0.5 <= d < 0.5, i.e. d <= 0 or |d| < 0.5: fires.
+// Outside that range (degenerate configurations) the candidate is verified against the predicate and walked.
+// Integer<->float conversions use the 2^23 magic-number form (FMA/ALU pipes) instead of the conversion unit.
 __device__ __forceinline__ int fire_clock(float until, int clock_now) {
   float t = fminf(fmaxf(until - 0.5f, 0.0f), 4.0e6f);
   float cf = FSUB(__fadd_rd(t, 8388608.0f), 8388608.0f) + 1.0f;   // floor(t) + 1 for 0 <= t < 2^23
-  if (!fires(until, cf)) {
-    int guard = 0;
-    do { cf += 1.0f; } while (!fires(until, cf) && ++guard < 64);
-  } else if (cf > 1.0f && fires(until, cf - 1.0f)) {
-    int guard = 0;
-    do { cf -= 1.0f; } while (cf > 1.0f && fires(until, cf - 1.0f) && ++guard < 64);
+  if (!(until >= 1.0f && until < 4.0e6f)) {
+    if (!fires(until, cf)) {
+      int guard = 0;
+      do { cf += 1.0f; } while (!fires(until, cf) && ++guard < 64);
+    } else if (cf > 1.0f && fires(until, cf - 1.0f)) {
+      int guard = 0;
+      do { cf -= 1.0f; } while (cf > 1.0f && fires(until, cf - 1.0f) && ++guard < 64);
+    }
   }
   int c = __float_as_int(cf + 12582912.0f) - 0x4B400000;           // exact for integers |c| < 2^22
   if (c <= clock_now) c = clock_now + 1;
