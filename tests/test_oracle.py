@@ -112,3 +112,52 @@ def test_soft_trace_symbol_rate():
     # ~520.83 symbols/s
     assert abs(len(t) / (len(s) / 22050.0) - 520.83) < 2.0
     assert np.all(np.abs(t["sym"]) <= 1.0)
+
+
+def test_batch_events_export_equals_the_single_stream_api():
+    """oracle_decode_batch_events (what the full-size GPU parity tests compare whole arrays against) must hand back
+    exactly what the single-receiver API reports, stream by stream, with and without samedec's EOF flush, for ragged
+    lengths and any thread count."""
+    from oracle import decode_batch_events
+    from oracle.pyoracle import default_config
+    recs = [load_golden_recording(n) for n in ("npt", "two_and_two")]
+    n = max(len(r) for r in recs)
+    a = np.zeros((3, n), np.int16)
+    a[0, :len(recs[0])] = recs[0]
+    a[1, :len(recs[1])] = recs[1]
+    a[2, :60000] = recs[0][:60000]
+    lengths = [len(recs[0]), len(recs[1]), 60000]
+    for flush in (False, True):
+        for threads in (1, 3):
+            ev, pay, _ = decode_batch_events(default_config(), a, threads, lengths=lengths, flush=flush)
+            assert np.all(np.diff(ev["stream"].astype(np.int64)) >= 0)
+            for s in range(3):
+                o = Oracle.samedec()
+                o.process_s16(a[s, :lengths[s]])
+                if flush:
+                    o.flush_samedec()
+                want = o.events()
+                got = ev[ev["stream"] == s]
+                assert got.size == len(want)
+                assert list(got["seq"]) == list(range(len(want)))
+                for g, w in zip(got, want):
+                    assert (g["kind"], g["err"], g["sample"], g["symbol_count"], g["parity_errors"], g["voting_bytes"]) == \
+                        (w.kind, w.err, w.sample, w.symbol_count, w.parity_errors, w.voting_bytes)
+                    assert bytes(pay[g["data_offset"]:g["data_offset"] + g["data_len"]]) == w.data
+
+
+def test_cpu_corpus_generator_is_deterministic_and_decodable():
+    """oracle/synth_cpu.hpp (the reference arm's corpus): same plans -> same samples for any thread count; the streams
+    carry their planned headers at 10 dB SNR."""
+    from oracle import decode_batch_events, synth_cpu
+    from oracle.pyoracle import default_config
+    from sameold_b200 import synth
+    plans = synth.plan_corpus(6, 22050, 45.0, first_stream=31)
+    x1 = synth_cpu(plans, 45 * 22050, 22050, 1)
+    x4 = synth_cpu(plans, 45 * 22050, 22050, 4)
+    assert np.array_equal(x1, x4) and x1.dtype == np.int16 and x1.shape == (6, 45 * 22050)
+    assert 3000 < x1[:, :20000].std() < 4500            # AWGN sigma 3663 before the first burst
+    ev, pay, _ = decode_batch_events(default_config(), x1, 2)
+    som = ev[ev["kind"] == 18]
+    texts = {int(e["stream"]): bytes(pay[e["data_offset"]:e["data_offset"] + e["data_len"]]).decode() for e in som}
+    assert sum(texts.get(i) == plans[i].header for i in range(6)) >= 5
