@@ -17,6 +17,7 @@ fn main() {
         ])
         .arg(&lib)
         .arg(csrc.join("same_kernels.cu"))
+        .arg(csrc.join("same_long.cu"))
         .arg(csrc.join("same_engine.cu"))
         .arg(csrc.join("same_multi.cu"))
         .status()

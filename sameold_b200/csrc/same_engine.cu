@@ -22,6 +22,14 @@ extern "C" cudaError_t same_launch_rx(const SameParams* p, const SameTaps* taps,
                                       const SameTiles* tiles, cudaStream_t stream);
 extern "C" cudaError_t same_launch_frontend(const SameParams* p, const int16_t* d_samples, const unsigned long long* d_offsets,
                                             const uint32_t* d_lengths, const SameTiles* tiles, cudaStream_t stream);
+extern "C" cudaError_t same_launch_rx_tilefed(const SameParams* p, const SameTaps2* taps2, const uint32_t* d_lengths,
+                                              const SameTiles* tiles, cudaStream_t stream);
+extern "C" cudaError_t same_long_launch_dc(const SameParams* p, const int16_t* d_src, uint32_t len, float* d, uint32_t* dc_next,
+                                           cudaStream_t stream);
+extern "C" cudaError_t same_long_launch_commit_dc(const SameParams* p, const uint32_t* dc_next, cudaStream_t stream);
+extern "C" cudaError_t same_long_launch_speculative(const SameParams* p, const SameTaps2* taps2, const float* d, uint32_t pos0,
+                                                    uint32_t end, float* yfull, float* gspec, float* g_in, float* soft,
+                                                    uint32_t* ctrl, cudaStream_t stream);
 extern "C" cudaError_t same_launch_evsort(const same_event* d_events, uint32_t n, uint32_t n_streams, uint32_t* d_cnt,
                                           uint32_t* d_minseq, uint32_t* d_start, same_event* d_sorted, uint32_t* d_bad,
                                           cudaStream_t stream);
@@ -85,8 +93,15 @@ struct same_engine {
   uint32_t lanes_per_warp = 32;   // streams per warp in the fast kernel (lane-sparse warps for small batches)
   int sm_count = 148;
   int kernel_auto = 0;            // fast-kernel flavour when force_generic == 0: 3 pipelined, 4 three-warp, 2 single-warp, 6 look-ahead
-  SameTiles tiles{nullptr, nullptr, 0u};   // split pipeline (kernel 5): front-end output, allocated on first use
+  SameTiles tiles{nullptr, nullptr, 0u, 32u, 1u};   // split pipeline (kernel 5): front-end output, allocated on first use
   size_t tiles_cap = 0;           // floats
+  // long-stream path (same_long.cu): one stream, long chunks
+  int long_stream = 1;            // option "long_stream"
+  float *ls_d = nullptr, *ls_y = nullptr, *ls_g = nullptr, *ls_soft = nullptr, *ls_gin = nullptr;
+  uint32_t* ls_ctrl = nullptr;    // device: {verified end, position reached, reason, -}
+  uint32_t* ls_hctrl = nullptr;   // pinned mirror + scratch
+  size_t ls_cap = 0;              // samples
+  uint64_t ls_spec_launches = 0, ls_fallback_launches = 0;
   bool saw_f32 = false;           // an f32 submit happened since create / reset(all): DC state may be non-integer -> generic kernel
   uint64_t lost_events = 0, lost_payloads = 0;
   same_derived derived;
@@ -252,6 +267,69 @@ int ensure_tiles(same_engine* e, uint32_t max_len) {
   return SAME_OK;
 }
 
+// ---- long-stream path: see same_long.cu ----
+constexpr uint32_t kLongMinSamples = 65536;     // shorter chunks take the ordinary kernels
+constexpr uint32_t kLongChunk = 1u << 24;       // samples per internal pass (bounds the scratch buffers: 16 B per sample)
+constexpr uint32_t kLongSpan = 8192;            // samples per fallback launch while the AGC is locked (inside a burst)
+
+int ensure_long(same_engine* e, size_t n) {
+  if (n > e->ls_cap) {
+    for (float** q : {&e->ls_d, &e->ls_y, &e->ls_g, &e->ls_soft, &e->ls_gin}) { if (*q) CK(e, cudaFree(*q)); *q = nullptr; }
+    e->ls_cap = 0;
+    CK(e, cudaMalloc(&e->ls_d, (n + 64) * sizeof(float)));
+    CK(e, cudaMalloc(&e->ls_y, (n + 128) * sizeof(float)));
+    CK(e, cudaMalloc(&e->ls_g, (n + 64) * sizeof(float)));
+    CK(e, cudaMalloc(&e->ls_soft, (n + 2 * 4096 + 64) * sizeof(float)));   // + two tiles: the sequential kernel stages ahead
+    CK(e, cudaMalloc(&e->ls_gin, (n / 2048 + 8) * sizeof(float)));
+    e->ls_cap = n;
+  }
+  if (!e->ls_ctrl) CK(e, cudaMalloc(&e->ls_ctrl, 4 * sizeof(uint32_t)));
+  if (!e->ls_hctrl) CK(e, cudaHostAlloc(&e->ls_hctrl, 8 * sizeof(uint32_t), cudaHostAllocDefault));
+  if (!e->tiles.dc_next) CK(e, cudaMalloc(&e->tiles.dc_next, (size_t)34 * e->p.layout.n_pad * sizeof(uint32_t)));
+  return SAME_OK;
+}
+
+// One stream, `len` device-resident s16 samples, on the compute stream.  Blocks the host (it steers the passes).
+int run_long(same_engine* e, const int16_t* d_src, uint32_t len, const uint32_t* d_len_scratch_unused) {
+  (void)d_len_scratch_unused;
+  const SameLayout& L = e->p.layout;
+  for (uint32_t base = 0; base < len; base += kLongChunk) {
+    const uint32_t n = std::min(kLongChunk, len - base);
+    int rc = ensure_long(e, n);
+    if (rc) return rc;
+    CK(e, same_long_launch_dc(&e->p, d_src + base, n, e->ls_d, e->tiles.dc_next, e->compute));
+    e->launches += 1;
+    uint32_t pos = 0;
+    while (pos < n) {
+      // is the AGC locked (inside a burst)?  then the samples are the ordinary kernel's, span by span
+      CK(e, cudaMemcpyAsync(e->ls_hctrl + 4, e->d_state + (size_t)F_FLAGS * L.n_pad, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->compute));
+      CK(e, cudaStreamSynchronize(e->compute));
+      if (e->ls_hctrl[4] & FLAG_AGC_LOCKED) {
+        const uint32_t span = std::min(kLongSpan, n - pos);
+        e->ls_hctrl[5] = span;
+        CK(e, cudaMemcpyAsync(e->ls_ctrl + 3, e->ls_hctrl + 5, sizeof(uint32_t), cudaMemcpyHostToDevice, e->compute));
+        SameTiles t{e->ls_d + pos, e->tiles.dc_next, span, 1u, 0u};
+        CK(e, same_launch_rx_tilefed(&e->p, &e->taps2, e->ls_ctrl + 3, &t, e->compute));
+        e->launches += 1; e->ls_fallback_launches += 1;
+        pos += span;
+        continue;
+      }
+      CK(e, same_long_launch_speculative(&e->p, &e->taps2, e->ls_d, pos, n, e->ls_y, e->ls_g, e->ls_gin, e->ls_soft, e->ls_ctrl,
+                                         e->compute));
+      e->launches += 4; e->ls_spec_launches += 1;
+      CK(e, cudaMemcpyAsync(e->ls_hctrl, e->ls_ctrl, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->compute));
+      CK(e, cudaStreamSynchronize(e->compute));
+      const uint32_t reached = e->ls_hctrl[1];
+      if (reached < pos || reached > n) return fail(e, SAME_ERR_CUDA, "long-stream pass reported an impossible position");
+      if (reached == pos && e->ls_hctrl[2] == 0u) return fail(e, SAME_ERR_CUDA, "long-stream pass made no progress");
+      pos = reached;
+    }
+    CK(e, same_long_launch_commit_dc(&e->p, e->tiles.dc_next, e->compute));
+    e->launches += 1;
+  }
+  return SAME_OK;
+}
+
 struct Submit2D { uint64_t row_stride = 0, col_start = 0, dpitch = 0; uint32_t n_cols = 0; bool on = false; };
 
 // sample_fmt: 0 = int16, 1 = float32
@@ -316,6 +394,18 @@ int submit_common(same_engine* e, const void* host_samples, const void* dev_samp
   CK(e, cudaEventRecord(e->t_k0, e->compute));
   // f32 input (now or earlier: the DC-blocker state may hold non-integers) needs the literal f32 recursion
   int kernel = e->saw_f32 ? 1 : (e->force_generic ? e->force_generic : e->kernel_auto);
+  // one stream, a long chunk: the long-stream path (time-parallel DC / AGC / matched filters, sequential timing loop)
+  if (e->long_stream && e->n_streams == 1 && !zeros && d_src && sample_fmt == 0 && !e->saw_f32 && e->force_generic == 0 &&
+      e->p.ntaps == 42 && e->p.dc_len == 16 && lengths[0] >= kLongMinSamples) {
+    int rc = run_long(e, static_cast<const int16_t*>(d_src) + offsets[0], lengths[0], b.d_len);
+    if (rc) return rc;
+    CK(e, cudaEventRecord(e->t_k1, e->compute));
+    CK(e, cudaEventRecord(b.consumed, e->compute));
+    b.used = true;
+    e->timed_kernel = true;
+    e->in_flight = true;
+    return SAME_OK;
+  }
   if (kernel == 5) {
     // split pipeline: the front end needs real samples (a zeros submit has none: the fused single-warp kernel takes it,
     // the resident state is the same) and a tile buffer for the longest chunk
@@ -565,6 +655,9 @@ void same_engine_destroy(same_engine* e) {
   for (auto& ev : e->stage_done) if (ev) cudaEventDestroy(ev);
   if (e->d_trace) cudaFree(e->d_trace);
   if (e->d_ids) cudaFree(e->d_ids);
+  for (float* q : {e->ls_d, e->ls_y, e->ls_g, e->ls_soft, e->ls_gin}) if (q) cudaFree(q);
+  if (e->ls_ctrl) cudaFree(e->ls_ctrl);
+  if (e->ls_hctrl) cudaFreeHost(e->ls_hctrl);
   if (e->tiles.d) cudaFree(e->tiles.d);
   if (e->tiles.dc_next) cudaFree(e->tiles.dc_next);
   for (cudaEvent_t ev : {e->t_h2d0, e->t_h2d1, e->t_k0, e->t_k1, e->t_sw0, e->t_sw1}) if (ev) cudaEventDestroy(ev);
@@ -817,6 +910,7 @@ int same_engine_set_option(same_engine* e, const char* key, int value) {
   }
 
   if (strcmp(key, "device_sort") == 0) { e->device_sort = value != 0; return SAME_OK; }
+  if (strcmp(key, "long_stream") == 0) { e->long_stream = value != 0; return SAME_OK; }
   if (strcmp(key, "lanes_per_warp") == 0) {
     if (!(value == 1 || value == 2 || value == 4 || value == 8 || value == 16 || value == 32))
       return fail(e, SAME_ERR_INVALID_ARG, "lanes_per_warp must be a power of two in 1..32");
@@ -830,6 +924,9 @@ int same_engine_get_option(same_engine* e, const char* key, int* value) {
   if (!e || !key || !value) return fail(e, SAME_ERR_INVALID_ARG, "null argument");
   if (strcmp(key, "kernel") == 0 || strcmp(key, "force_generic") == 0) { *value = e->force_generic; return SAME_OK; }
   if (strcmp(key, "device_sort") == 0) { *value = e->device_sort; return SAME_OK; }
+  if (strcmp(key, "long_stream") == 0) { *value = e->long_stream; return SAME_OK; }
+  if (strcmp(key, "long_stream_passes") == 0) { *value = (int)std::min<uint64_t>(e->ls_spec_launches, 0x7fffffff); return SAME_OK; }
+  if (strcmp(key, "long_stream_fallback_spans") == 0) { *value = (int)std::min<uint64_t>(e->ls_fallback_launches, 0x7fffffff); return SAME_OK; }
   if (strcmp(key, "lanes_per_warp") == 0) { *value = (int)e->lanes_per_warp; return SAME_OK; }
   if (strcmp(key, "kernel_selected") == 0) {
     const bool fast_geometry = e->p.ntaps == 42 && e->p.dc_len == 16;

@@ -339,13 +339,13 @@ __device__ __forceinline__ uint32_t eq_byte_impl(const SameParams& p, uint32_t s
 }
 
 // rate-generic equalizer (any order up to 16/16): out of line, arrays in local memory
-__device__ __noinline__ uint32_t eq_byte_generic(const SameParams& p, uint32_t s, const float* S, uint32_t& flags,
+static __device__ __noinline__ uint32_t eq_byte_generic(const SameParams& p, uint32_t s, const float* S, uint32_t& flags,
                                                  uint32_t& train_sa, uint32_t& train_cnt) {
   return eq_byte_impl<SAME_MAX_EQ, SAME_MAX_EQ, false>(p, s, S, flags, train_sa, train_cnt);
 }
 
 // Equalizer::reset  equalize.rs:191-196 (mode is kept)
-__device__ __noinline__ void eq_reset(const SameParams& p, uint32_t s) {
+static __device__ __noinline__ void eq_reset(const SameParams& p, uint32_t s) {
   const SameLayout& L = p.layout;
   uint32_t* st = p.state32 + s;
   for (uint32_t i = 0; i < p.eq_nff; ++i) {

@@ -142,6 +142,10 @@ struct SameTiles {
   float* d;
   uint32_t* dc_next;
   uint32_t n_max;      // samples per stream in the tile buffer (multiple of 32)
+  uint32_t stride;     // floats between consecutive samples of one stream: 32 (lane-major tiles) or 1 (one dense stream:
+                       // the long-stream path, same_long.cu)
+  uint32_t commit_dc;  // the tile-fed loop kernel copies dc_next into the state words when it finishes (0: the caller
+                       // does it later -- the kernel only covers a span of the front end's output)
 };
 
 struct SameTaps2 {                // the same taps as (re, im) pairs for the packed-FFMA2 matched filter

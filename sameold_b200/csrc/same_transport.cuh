@@ -41,7 +41,7 @@ __device__ __forceinline__ void copy_words(uint8_t* __restrict__ dst, const uint
 
 // Everything is passed by value: a by-reference argument to a noinline function would force the caller's lane state
 // out of registers into local memory for the whole kernel.
-__device__ __noinline__ void emit_event_impl(const SameParams& p, uint32_t stream, uint32_t seq, uint32_t kind,
+static __device__ __noinline__ void emit_event_impl(const SameParams& p, uint32_t stream, uint32_t seq, uint32_t kind,
                                              uint32_t err, unsigned long long n, unsigned long long symcount,
                                              const uint8_t* data, uint32_t data_len, uint32_t copy_len, uint32_t parity,
                                              uint32_t voting, uint32_t flags) {
@@ -153,7 +153,7 @@ __device__ __forceinline__ uint32_t framer_input(const SameParams& p, StreamBlob
 __device__ __forceinline__ bool is_alpha(uint32_t c) { return (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z'); }
 __device__ __forceinline__ bool is_digit(uint32_t c) { return c >= '0' && c <= '9'; }
 
-__device__ __noinline__ bool check_header(const uint8_t* h, uint32_t n, uint32_t& off_time, uint32_t& hdr_len) {
+static __device__ __noinline__ bool check_header(const uint8_t* h, uint32_t n, uint32_t& off_time, uint32_t& hdr_len) {
   if (n < 13) return false;
   if (!(h[0] == 'Z' && h[1] == 'C' && h[2] == 'Z' && h[3] == 'C' && h[4] == '-')) return false;
   if (!(is_alpha(h[5]) && is_alpha(h[6]) && is_alpha(h[7]) && h[8] == '-' && is_alpha(h[9]) && is_alpha(h[10]) &&
@@ -217,7 +217,7 @@ __device__ __forceinline__ void recompute_next_deadline(const StreamBlob* b, Tra
 }
 
 // assembler.rs:357-363
-__device__ __noinline__ void prune_history(StreamBlob* b, Transport& t, unsigned long long now) {
+static __device__ __noinline__ void prune_history(StreamBlob* b, Transport& t, unsigned long long now) {
   uint32_t w = 0;
   for (uint32_t k = 0; k < t.hist_n; ++k) {
     if (b->hist[k].deadline <= now) continue;
@@ -240,7 +240,7 @@ __device__ __noinline__ void prune_history(StreamBlob* b, Transport& t, unsigned
 // combiner.rs:154-203 + 32-80.  Returns false for `None`.  The estimate is left in b->est[0..good_len).
 // The three bursts are read one 32-bit word (4 message bytes) at a time and the estimate / burst-count / bit-error
 // arrays are written one word at a time; the per-byte voting logic itself is the reference's, on register values.
-__device__ __noinline__ bool combine(StreamBlob* b, const Transport& t, MsgResult& res) {
+static __device__ __noinline__ bool combine(StreamBlob* b, const Transport& t, MsgResult& res) {
   const uint32_t nb = min(t.hist_n, 3u);
   const uint32_t l0 = nb > 0 ? b->hist[0].len : 0u, l1 = nb > 1 ? b->hist[1].len : 0u, l2 = nb > 2 ? b->hist[2].len : 0u;
   const uint32_t* w0 = reinterpret_cast<const uint32_t*>(b->hist[0].data);
@@ -318,7 +318,7 @@ __device__ __noinline__ bool combine(StreamBlob* b, const Transport& t, MsgResul
 }
 
 // PendingResult::accept  assembler.rs:294-331.  For SOM the text is b->est[0..len).
-__device__ __noinline__ void pending_accept(const SameParams& p, StreamBlob* b, Transport& t, const MsgResult& r,
+static __device__ __noinline__ void pending_accept(const SameParams& p, StreamBlob* b, Transport& t, const MsgResult& r,
                                             unsigned long long now) {
   unsigned long long dl = (r.kind == 1) ? now : now + p.interburst_symbols;
   bool store;
@@ -339,7 +339,7 @@ __device__ __noinline__ void pending_accept(const SameParams& p, StreamBlob* b, 
 
 // Assembler::idle  assembler.rs:205-234.  Returns transport kind (0 Idle, 1 Assembling, 2 Message); for Message the
 // result is in `out` and its text in b->pending_text.
-__device__ __noinline__ uint32_t assembler_idle(const SameParams& p, StreamBlob* b, Transport& t,
+static __device__ __noinline__ uint32_t assembler_idle(const SameParams& p, StreamBlob* b, Transport& t,
                                                 unsigned long long now, MsgResult& out) {
   prune_history(b, t, now);
   uint32_t kind;
@@ -360,7 +360,7 @@ __device__ __noinline__ uint32_t assembler_idle(const SameParams& p, StreamBlob*
 }
 
 // Assembler::assemble  assembler.rs:154-184.  `burst` = blob->burst[0..min(len,CAP)).
-__device__ __noinline__ uint32_t assembler_assemble(const SameParams& p, StreamBlob* b, Transport& t, uint32_t burst_len,
+static __device__ __noinline__ uint32_t assembler_assemble(const SameParams& p, StreamBlob* b, Transport& t, uint32_t burst_len,
                                                     unsigned long long now, MsgResult& out) {
   if (burst_len == 0) return assembler_idle(p, b, t, now, out);
   prune_history(b, t, now);

@@ -495,6 +495,61 @@ def test_long_single_stream_in_time_chunks():
     assert rx.input_sample_counters()[0] == len(stream)
 
 
+def test_long_stream_path_is_bit_exact_and_used():
+    """One stream, chunks of >= 65536 samples take the long-stream path (same_long.cu): DC blocker, AGC and matched
+    filters time-parallel (the AGC speculatively per block, every hand-over gain verified bitwise), the timing loop and
+    everything after it sequential on one lane; bursts (AGC locked) by the ordinary tile-fed kernel.  Events must equal
+    the oracle's and the ordinary kernels', across chunk boundaries that fall inside bursts, and the path must really
+    have run (speculative passes and fallback spans counted)."""
+    _torch()
+    b = sb.SameReceiverBuilder.samedec(22050)
+    rng = np.random.default_rng(17)
+    streams = [load_golden_recording(n) for n in NAMES]
+    parts = []
+    for i in range(3):       # 3 SAME events with minutes of noise between them
+        parts.append(synth.render_numpy(synth.plan_stream(700 + i, seconds=60.0), 60 * 22050))
+        parts.append(np.clip(np.rint(rng.normal(0.0, 3663.0, 100 * 22050 + 977 * i)), -32768, 32767).astype(np.int16))
+    streams.append(np.concatenate(parts))
+    silence = np.zeros(20 * 22050, np.int16)                       # exact zeros: the gain runs into its clamp
+    streams.append(np.concatenate([silence, streams[1], silence]))
+    for si, x in enumerate(streams):
+        o = Oracle(oracle_cfg_from(b))
+        o.process_s16(x)
+        want = o.events()
+        for chunking in ("whole", "ragged"):
+            rx = b.build_batch(1)
+            assert rx.get_option("long_stream") == 1
+            got = []
+            if chunking == "whole":
+                got = rx.process([x])[0]
+            else:
+                i = 0
+                while i < len(x):
+                    k = int(rng.integers(65536, 400000))
+                    got.extend(rx.process([x[i:i + k]])[0])
+                    i += k
+            assert_events_equal(got, want, f"long-stream path, stream {si}, {chunking}")
+            assert rx.get_option("long_stream_passes") >= 1
+            if any(e.kind == 3 for e in want):
+                assert rx.get_option("long_stream_fallback_spans") >= 1
+            assert rx.input_sample_counters()[0] == len(x)
+        # and switching the path off gives the same events (ordinary pipelined kernel)
+        rx = b.build_batch(1)
+        rx.set_option("long_stream", 0)
+        assert_events_equal(rx.process([x])[0], want, f"ordinary path, stream {si}")
+        assert rx.get_option("long_stream_passes") == 0
+    # a long chunk, then short ones (ordinary kernels), then a long one again: one resident state for all
+    x = streams[3]
+    o = Oracle(oracle_cfg_from(b))
+    o.process_s16(x)
+    rx = b.build_batch(1)
+    got, i = [], 0
+    for k in (300000, 1000, 31, 70000, 5000, 10 ** 9):
+        got.extend(rx.process([x[i:i + k]])[0])
+        i += k
+    assert_events_equal(got, o.events(), "long and short chunks mixed")
+
+
 def test_lane_sparse_warps_give_identical_results():
     """Small batches run with fewer streams per warp (latency-bound regime); the mapping must not change results."""
     _torch()
