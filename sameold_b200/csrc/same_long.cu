@@ -12,10 +12,11 @@
 //      same_long_verify_kernel   first block whose hand-over fails -> end of the range that may be consumed.
 //   C  same_long_mf_kernel    the mark/space matched filters (demod.rs:156-164) at EVERY sample position of that AGC
 //                             output, time-parallel: 21x the arithmetic of the sequential receiver, in parallel.
-//   D  same_long_seq_kernel   the timing loop, squelch, equalizer, framer and transport (A5-A9), strictly sequential on
-//                             one lane, picking its soft symbols out of C's output (staged through shared memory by the
-//                             warp): ~250 cycles per TED round instead of ~1500.  It stops when the symbol stages lock
-//                             the AGC (sync found: a burst begins), at the end of the verified range, or at the end.
+//   D  same_long_seq_kernel   the timing loop (A5) strictly sequential on one lane, picking its soft symbols out of C's
+//                             output (staged through shared memory), and the squelch, equalizer, framer and transport
+//                             (A6-A9) on a second warp, one ring of symbol records behind: ~250 cycles per TED round
+//                             instead of ~1500.  It stops when the symbol stages lock the AGC (sync found: a burst
+//                             begins) or reset the timing loop, at the end of the verified range, or at the end.
 //   burst / unverified spans  the ordinary tile-fed single-warp kernel (same_rx_fast_kernel<true>) on A's output, until
 //                             the AGC is unlocked again; then B-D restart from the true state.
 // The speculation in B never decides anything: a block is used only after its hand-over gain was verified, and D's
@@ -149,68 +150,142 @@ __global__ void __launch_bounds__(256) same_long_mf_kernel(const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------------------------- D
+// Two warps, one lane each doing sequential work, pipelined:
+//   warp T  the timing loop (A5): picks its soft symbol out of the staged tile (the warp's other lanes stage tiles one
+//           ahead with 16-byte asynchronous copies), TED, PI loop, next fire clock; every emitted symbol goes into a ring
+//           of records together with the loop state it left behind.
+//   warp S  the symbol stages (A6-A9) on those records: squelch, equalizer, framer, events, transport.
+// Until the squelch finds sync nothing the symbol stages do feeds back into the timing loop (receiver.rs:423-438,
+// 479-490 all hang off sync / carrier-drop / burst-end), so T may run ahead of S by the ring.  When S's symbol locks the
+// AGC (sync found: a burst begins) or resets the timing loop (end()), the record's state IS the receiver's state at that
+// symbol: S stops the kernel there and whatever T did beyond it is dropped (T touches no global state).
 // ctrl[0] in: end of the verified range (absolute position in the submit).  Out: ctrl[1] = position reached,
-// ctrl[2] = why it stopped (0 range end, 1 AGC locked by the symbol stages).
-__global__ void __launch_bounds__(32) same_long_seq_kernel(const __grid_constant__ SameParams p, const float* __restrict__ soft,
+// ctrl[2] = why it stopped (0 range end, 1 AGC locked by the symbol stages, 2 timing loop reset by them).
+#define LS_RING 64
+struct LsRec { uint32_t pos; float zero, sym, until, pavg, pinst, ted0; uint32_t pad; };
+
+__global__ void __launch_bounds__(64) same_long_seq_kernel(const __grid_constant__ SameParams p, const float* __restrict__ soft,
                                                            const float* __restrict__ yfull, const float* __restrict__ gspec,
                                                            const uint32_t pos0, uint32_t* __restrict__ ctrl) {
   __shared__ __align__(16) float tile[2][LS_TILE];
+  __shared__ LsRec ring[LS_RING];
+  __shared__ volatile uint32_t sh_head, sh_tail, sh_stop, sh_tdone;
+  __shared__ float t_final[8];          // T's loop state at the end of the range: until, pavg, pinst, ted0, ted1, ted2, tedcnt, clock
+  __shared__ uint32_t t_pos;
   const SameLayout& L = p.layout;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int role = threadIdx.x >> 5;   // 0 = T, 1 = S
   uint32_t* st = p.state32;            // stream 0
   StreamBlob* blob = p.blobs;
   const uint32_t range = ctrl[0] - pos0;   // samples that may be consumed
+  if (threadIdx.x == 0) { sh_head = 0u; sh_tail = 0u; sh_stop = 0u; sh_tdone = 0u; }
+  __syncthreads();
 
   Lane a;
   lane_load(a, p, st, 0u);
-  uint32_t pos = 0;                    // relative to pos0
-  int cfire = fire_clock(a.until, a.clock);
-  uint32_t why = 0, done = 0;
+  uint32_t why = 0, stop_pos = 0;
 
-  // The warp stages soft[tbase .. tbase + LS_TILE) (soft index = relative position) with 16-byte asynchronous copies,
-  // one tile ahead of the tile lane 0 is working on (`soft` is padded by a tile: reading past `range` is harmless,
-  // those values are never used).
-  const auto stage = [&](uint32_t tbase, int buf) {
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tile[buf][0]);
+  if (role == 0) {
+    // ================================================ T: timing loop ================================================
+    uint32_t pos = 0;                    // relative to pos0
+    int cfire = fire_clock(a.until, a.clock);
+    uint32_t done = 0, head = 0, tail_seen = 0;
+    const auto stage = [&](uint32_t tbase, int buf) {   // `soft` is padded by two tiles: reading past `range` is harmless
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tile[buf][0]);
 #pragma unroll 4
-    for (uint32_t j = (uint32_t)lane * 4u; j < LS_TILE; j += 128u)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + j * 4u), "l"(soft + tbase + j) : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  stage(0u, 0);
-  int buf = 0;
-  for (uint32_t tbase = 0; !done; tbase += LS_TILE, buf ^= 1) {
-    stage(tbase + LS_TILE, buf ^ 1);
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncwarp();
-    if (lane == 0) {
-      const float* tl = &tile[buf][0];
-      while (true) {
-        const uint32_t next = pos + (uint32_t)(cfire - a.clock);      // position of the next TED instant
-        if (next > range) {                                            // not inside the range: consume what is left
-          a.clock += (int)(range - pos);
-          pos = range;
-          done = 1;
-          break;
+      for (uint32_t j = (uint32_t)lane * 4u; j < LS_TILE; j += 128u)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + j * 4u), "l"(soft + tbase + j) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(0u, 0);
+    int buf = 0;
+    for (uint32_t tbase = 0; !done; tbase += LS_TILE, buf ^= 1) {
+      stage(tbase + LS_TILE, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        const float* tl = &tile[buf][0];
+        if (sh_stop) done = 1;                                           // checked per tile and while the ring is full
+        while (!done) {
+          const uint32_t next = pos + (uint32_t)(cfire - a.clock);      // position of the next TED instant
+          if (next > range) {                                            // not inside the range: consume what is left
+            a.clock += (int)(range - pos);
+            pos = range;
+            done = 1;
+            break;
+          }
+          if (next >= tbase + LS_TILE) break;                            // in the next tile
+          a.clock = cfire;
+          pos = next;
+          const float s_in = tl[pos - tbase];
+          const float rem = FSUB(a.until, (float)a.clock);               // receiver.rs:352
+          a.clock = 0;
+          const bool have_sym = ted_step(a, p, s_in, rem);
+          cfire = fire_clock(a.until, 0);
+          if (have_sym) {
+            if (head - tail_seen >= (uint32_t)LS_RING) {                   // ring full as far as T knows: look again, wait for S
+              while (head - (tail_seen = sh_tail) >= (uint32_t)LS_RING) { if (sh_stop) { done = 1; break; } }
+              if (done) break;
+            }
+            // volatile stores: a thread's shared-memory stores are performed in program order, so S, which reads the
+            // head counter first, sees a complete record
+            volatile float* q = reinterpret_cast<volatile float*>(&ring[head & (LS_RING - 1)]);
+            q[1] = a.ted1; q[2] = a.ted2; q[3] = a.until; q[4] = a.pavg; q[5] = a.pinst; q[6] = a.ted0;
+            reinterpret_cast<volatile uint32_t*>(q)[0] = pos;
+            head += 1u;
+            sh_head = head;
+          }
         }
-        if (next >= tbase + LS_TILE) break;                            // in the next tile
-        a.clock = cfire;
-        pos = next;
-        const float s_in = tl[pos - tbase];
-        const float rem = FSUB(a.until, (float)a.clock);               // receiver.rs:352
-        a.clock = 0;
-        const bool have_sym = ted_step(a, p, s_in, rem);
-        cfire = fire_clock(a.until, 0);
-        if (have_sym) symbol_step(a, p, 0u, st, blob, a.ted1, a.ted2, a.n0 + pos);
-        if (a.flags & FLAG_AGC_LOCKED) { done = 1; why = 1; break; }   // a burst begins: the AGC trajectory ends here
+        if (done) {
+          t_final[0] = a.until; t_final[1] = a.pavg; t_final[2] = a.pinst; t_final[3] = a.ted0; t_final[4] = a.ted1;
+          t_final[5] = a.ted2; t_final[6] = __uint_as_float(a.tedcnt); t_final[7] = __int_as_float(a.clock);
+          t_pos = pos;
+          __threadfence_block();
+          sh_tdone = 1u;
+        }
+      }
+      done = __shfl_sync(0xffffffffu, done, 0);
+      __syncwarp();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else if (lane == 0) {
+    // ================================================ S: symbol stages ================================================
+    uint32_t tail = 0;
+    while (true) {
+      uint32_t head = sh_head;
+      if (tail == head) {
+        if (sh_tdone) { head = sh_head; if (tail == head) break; }
+        else continue;
+      }
+      LsRec r;
+      {
+        const volatile float* q = reinterpret_cast<const volatile float*>(&ring[tail & (LS_RING - 1)]);
+        r.pos = reinterpret_cast<const volatile uint32_t*>(q)[0];
+        r.zero = q[1]; r.sym = q[2]; r.until = q[3]; r.pavg = q[4]; r.pinst = q[5]; r.ted0 = q[6];
+      }
+      a.until = r.until; a.pavg = r.pavg; a.pinst = r.pinst;
+      a.ted0 = r.ted0; a.ted1 = r.zero; a.ted2 = r.sym; a.tedcnt = 1u; a.clock = 0;
+      symbol_step(a, p, 0u, st, blob, r.zero, r.sym, a.n0 + r.pos);
+      tail += 1u;
+      sh_tail = tail;
+      if ((a.flags & FLAG_AGC_LOCKED) || a.tedcnt != 1u) {       // sync found (AGC locked) or end() reset the timing loop
+        why = (a.flags & FLAG_AGC_LOCKED) ? 1u : 2u;
+        stop_pos = r.pos;
+        __threadfence_block();
+        sh_stop = 1u;
+        break;
       }
     }
-    done = __shfl_sync(0xffffffffu, done, 0);
-    __syncwarp();
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  if (lane != 0) return;
-  // ---- state out: gain at pos, the 42 AGC outputs before pos, everything else as usual ----
+  __syncthreads();
+  if (threadIdx.x != 32) return;
+  // ---- state out (S's lane): the symbol stages' state + the timing loop's state at the stop symbol / at the range end ----
+  uint32_t pos = stop_pos;
+  if (why == 0u) {
+    a.until = t_final[0]; a.pavg = t_final[1]; a.pinst = t_final[2]; a.ted0 = t_final[3]; a.ted1 = t_final[4];
+    a.ted2 = t_final[5]; a.tedcnt = __float_as_uint(t_final[6]); a.clock = __float_as_int(t_final[7]);
+    pos = t_pos;
+  }
   if (pos > 0u) a.g = gspec[pos - 1u];
   lane_store(a, p, st, a.n0 + pos);
   for (int i = 0; i < FAST_NTAPS; ++i) LANE_ST(st, L, L.win + i) = __float_as_uint(yfull[pos + i]);
@@ -248,6 +323,6 @@ extern "C" cudaError_t same_long_launch_speculative(const SameParams* p, const S
   if (blocks > 1u)
     same_dev::same_long_verify_kernel<<<(blocks - 1u + 127u) / 128u, 128, 0, stream>>>(gspec, g_in, pos0, end, ctrl);
   same_dev::same_long_mf_kernel<<<(n + 255u) / 256u, 256, 0, stream>>>(*taps2, yfull, n, soft);
-  same_dev::same_long_seq_kernel<<<1, 32, 0, stream>>>(*p, soft, yfull, gspec, pos0, ctrl);
+  same_dev::same_long_seq_kernel<<<1, 64, 0, stream>>>(*p, soft, yfull, gspec, pos0, ctrl);
   return cudaGetLastError();
 }
