@@ -233,7 +233,7 @@ def kernel_source_sha16():
     taken from, so a stale capture is dropped instead of silently reported."""
     import hashlib
     h = hashlib.sha256()
-    for f in ("same_kernels.cu", "same_lane.cuh", "same_transport.cuh", "same_params.h"):
+    for f in ("same_kernels.cu", "same_fast.cuh", "same_lane.cuh", "same_transport.cuh", "same_params.h"):
         with open(os.path.join(ROOT, "sameold_b200", "csrc", f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()[:16]

@@ -78,7 +78,7 @@ def main():
         import os
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
         hh = hashlib.sha256()
-        for f in ("same_kernels.cu", "same_lane.cuh", "same_transport.cuh", "same_params.h"):
+        for f in ("same_kernels.cu", "same_fast.cuh", "same_lane.cuh", "same_transport.cuh", "same_params.h"):
             hh.update(open(os.path.join(root, "sameold_b200", "csrc", f), "rb").read())
         json.dump({"streams": streams, "seconds": seconds, "report": os.path.basename(rep),
                    "captured": datetime.date.today().isoformat(), "kernel_src_sha16": hh.hexdigest()[:16],
