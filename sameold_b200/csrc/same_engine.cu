@@ -290,8 +290,7 @@ int ensure_long(same_engine* e, size_t n) {
 }
 
 // One stream, `len` device-resident s16 samples, on the compute stream.  Blocks the host (it steers the passes).
-int run_long(same_engine* e, const int16_t* d_src, uint32_t len, const uint32_t* d_len_scratch_unused) {
-  (void)d_len_scratch_unused;
+int run_long(same_engine* e, const int16_t* d_src, uint32_t len) {
   const SameLayout& L = e->p.layout;
   for (uint32_t base = 0; base < len; base += kLongChunk) {
     const uint32_t n = std::min(kLongChunk, len - base);
@@ -397,7 +396,7 @@ int submit_common(same_engine* e, const void* host_samples, const void* dev_samp
   // one stream, a long chunk: the long-stream path (time-parallel DC / AGC / matched filters, sequential timing loop)
   if (e->long_stream && e->n_streams == 1 && !zeros && d_src && sample_fmt == 0 && !e->saw_f32 && e->force_generic == 0 &&
       e->p.ntaps == 42 && e->p.dc_len == 16 && lengths[0] >= kLongMinSamples) {
-    int rc = run_long(e, static_cast<const int16_t*>(d_src) + offsets[0], lengths[0], b.d_len);
+    int rc = run_long(e, static_cast<const int16_t*>(d_src) + offsets[0], lengths[0]);
     if (rc) return rc;
     CK(e, cudaEventRecord(e->t_k1, e->compute));
     CK(e, cudaEventRecord(b.consumed, e->compute));

@@ -89,7 +89,6 @@ __global__ void same_long_agc_kernel(const __grid_constant__ SameParams p, const
                                      float* __restrict__ g_in) {
   const SameLayout& L = p.layout;
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k == 0 && threadIdx.x == 0) {}   // (block 0 also copies the window below)
   const unsigned long long sk64 = (unsigned long long)pos0 + (unsigned long long)k * LS_BLOCK;
   if (sk64 >= end) return;
   const uint32_t sk = (uint32_t)sk64;

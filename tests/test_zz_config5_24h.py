@@ -1,9 +1,10 @@
 """BASELINE config 5 at full length: ONE continuous 24 h stream (1 905 120 000 samples, 3.81 GB) with sparse SAME events,
 decoded by a one-stream engine in 10-minute chunks, against the CPU oracle event for event.
 
-A single stream is strictly sequential (receiver.rs:243): this is one lane of one warp, the latency of one dependent
-chain — "replicas only" in DESIGN.md; the test pins parity over 24 h of state carried across 144 submits and reports
-the single-stream realtime factor.  Runs last (file name) because it is the longest test (~2-3 min).
+A single stream is strictly sequential in its timing loop (receiver.rs:243); everything in front of the loop runs
+time-parallel in the engine's long-stream path (same_long.cu, DESIGN.md §4: speculative block AGC with bitwise-verified
+hand-over, dense matched filters, bursts by the ordinary kernels).  The test pins parity over 24 h of state carried
+across 144 submits and reports the single-stream realtime factor.  Runs last (file name): the longest test (~1 min).
 SAME_TEST_HOURS overrides the length (e.g. 2 for a quick check)."""
 import os
 import time
@@ -52,7 +53,7 @@ def test_single_24h_stream_vs_oracle():
     want = o.events()
     n_msgs = sum(1 for e in want if e.kind in (18, 19))
     print(f"\nconfig 5: {hours:g} h stream, {len(plan.burst_starts)} bursts planned, {len(want)} events, {n_msgs} messages; "
-          f"engine {gpu_s:.1f} s = {hours * 3600 / gpu_s:.0f}x realtime (one lane); oracle {cpu_s:.1f} s = "
+          f"engine {gpu_s:.1f} s = {hours * 3600 / gpu_s:.0f}x realtime (long-stream path); oracle {cpu_s:.1f} s = "
           f"{hours * 3600 / cpu_s:.0f}x realtime (one core)")
     assert n_msgs >= 2 * (len(plan.burst_starts) // 6) - 2, "nearly every event yields a header and an EOM"
     assert [e.key() for e in got] == [e.key() for e in want]
