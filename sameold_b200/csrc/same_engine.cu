@@ -911,8 +911,7 @@ int same_engine_set_option(same_engine* e, const char* key, int value) {
   if (strcmp(key, "device_sort") == 0) { e->device_sort = value != 0; return SAME_OK; }
   if (strcmp(key, "long_stream") == 0) { e->long_stream = value != 0; return SAME_OK; }
   if (strcmp(key, "lanes_per_warp") == 0) {
-    if (!(value == 1 || value == 2 || value == 4 || value == 8 || value == 16 || value == 32))
-      return fail(e, SAME_ERR_INVALID_ARG, "lanes_per_warp must be a power of two in 1..32");
+    if (value < 1 || value > 32) return fail(e, SAME_ERR_INVALID_ARG, "lanes_per_warp must be in 1..32");
     e->lanes_per_warp = (uint32_t)value;
     return SAME_OK;
   }
