@@ -262,6 +262,36 @@ __global__ void __launch_bounds__(64) same_long_seq_kernel(const __grid_constant
         r.pos = reinterpret_cast<const volatile uint32_t*>(q)[0];
         r.zero = q[1]; r.sym = q[2]; r.until = q[3]; r.pavg = q[4]; r.pinst = q[5]; r.ted0 = q[6];
       }
+      // The quiet symbol (nearly all of a long stream): no carrier, framer idle, nothing pending in the transport layer
+      // and this symbol does not complete the sync word.  Then symbol_squelch + symbol_finish reduce to the squelch's
+      // own bookkeeping (same expressions as same_lane.cuh:symbol_squelch, codesquelch.rs:228-304,421-428,483-488) --
+      // written out here because a single lane pays for every instruction of the select-based general form.
+      bool quiet = false;
+      if (p.trace == nullptr && a.byteclk < 0 && a.fr.st == 0u && a.link_last == 0u) {
+        const uint32_t nd = (a.sq_data >> 1) | ((r.sym >= 0.0f) ? 0x80000000u : 0u);
+        const uint32_t cerr = __popc(nd ^ p.sq_sync_word);
+        const float pw = fmaxf(FADD(a.sq_power, FMUL(FSUB(FMUL(r.sym, r.sym), a.sq_power), p.sq_bw)), 0.0f);
+        const unsigned long long sc = a.symcount + 1ull;
+        const unsigned long long n = a.n0 + r.pos;
+        const bool acquire = sc >= 32ull && !(a.flags & FLAG_SQ_LOCK) && cerr <= p.sq_max_err && pw >= p.sq_open;
+        const bool transport_due = (a.tr.have_eom && n > a.tr.eom_at) || sc >= a.tr.next_deadline ||
+                                   ((a.tr.hist_n ? 1u : 0u) != a.tr.tr_state);
+        if (!acquire && !transport_due) {
+          LANE_ST(st, L, L.sqh + (a.sq_head & 63u)) = __float_as_uint(r.zero);
+          LANE_ST(st, L, L.sqh + ((a.sq_head + 1u) & 63u)) = __float_as_uint(r.sym);
+          a.sq_head = (a.sq_head + 2u) & 63u;
+          a.sq_data = nd;
+          a.sq_power = pw;
+          a.sq_pflags = (a.sq_pflags >> 1) | ((pw >= p.sq_close) ? 0x80000000u : 0u);
+          a.symcount = sc;
+          quiet = true;
+        }
+      }
+      if (quiet) {
+        tail += 1u;
+        sh_tail = tail;
+        continue;
+      }
       a.until = r.until; a.pavg = r.pavg; a.pinst = r.pinst;
       a.ted0 = r.ted0; a.ted1 = r.zero; a.ted2 = r.sym; a.tedcnt = 1u; a.clock = 0;
       symbol_step(a, p, 0u, st, blob, r.zero, r.sym, a.n0 + r.pos);
