@@ -1,12 +1,14 @@
 #!/bin/bash
-# round-2 final validation: GPU tests, smoke, bench (both arms, config 5), ncu launch list and the config-3 traffic capture
+# round-2 final validation: GPU tests, smoke, bench (config 3 + config-4 leg, config 5), ncu launch list and the config-3
+# traffic capture (profiles/rx_kernel_traffic.json via tools/ncu_summary.py --traffic-json)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 ( time timeout 1500 python -m pytest tests -m gpu -q -x --durations=6 ) > gpurun_out/r2z_tests.txt 2>&1
 tail -12 gpurun_out/r2z_tests.txt
 ( time timeout 300 python -c "import __graft_entry__ as g; g.smoke()" ) > gpurun_out/r2z_smoke.txt 2>&1; grep -i smoke gpurun_out/r2z_smoke.txt
-( time timeout 600 python bench.py ) > gpurun_out/r2z_bench.json 2> gpurun_out/r2z_bench.err; tail -c 500 gpurun_out/r2z_bench.json; tail -2 gpurun_out/r2z_bench.err
-( time timeout 600 python bench.py --config 5 --hours 24 ) > gpurun_out/r2z_config5.json 2> gpurun_out/r2z_config5.err; tail -c 700 gpurun_out/r2z_config5.json; tail -2 gpurun_out/r2z_config5.err
+( time timeout 600 python bench.py ) > gpurun_out/r2z_bench.json 2> gpurun_out/r2z_bench.err; tail -c 300 gpurun_out/r2z_bench.json; tail -2 gpurun_out/r2z_bench.err
+( time timeout 600 python bench.py --config 5 --hours 24 ) > gpurun_out/r2z_config5.json 2> gpurun_out/r2z_config5.err; tail -c 600 gpurun_out/r2z_config5.json; tail -2 gpurun_out/r2z_config5.err
+if [ "$1" = "ncu" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2z_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/r2z_launches.log 2>&1; tail -1 gpurun_out/r2z_launches.log | cut -c1-200
 cat > /tmp/ncu_job.py <<'PY'
 import sys, numpy as np, torch
@@ -22,3 +24,4 @@ rx = sb.SameReceiverBuilder.samedec(22050).build_batch(ns)
 rx.reset(); rx.submit_device(buf.data_ptr(), ns * stride, off, ln); rx.sync(); rx.drain_raw()
 PY
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'same_rx_pipe' -c 1 -o gpurun_out/r2z_pipe_config3 python /tmp/ncu_job.py > gpurun_out/r2z_ncu1.log 2>&1; tail -1 gpurun_out/r2z_ncu1.log
+fi
