@@ -10,6 +10,7 @@ from .pyoracle import (  # noqa: F401
     build_oracle,
     decode_batch_events,
     synth_cpu,
+    agc_block_model,
     BATCH_EVENT_DTYPE,
     load_golden_recording,
     GOLDEN_DIR,

@@ -136,6 +136,8 @@ def _lib():
         lib.oracle_batch_seconds.argtypes = [C.c_void_p]
         lib.oracle_batch_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.oracle_batch_free.argtypes = [C.c_void_p]
+        lib.oracle_agc_block_model.argtypes = [C.POINTER(OracleConfig), C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_float,
+                                               C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         lib.oracle_synth_generate.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int]
         _LIB = lib
@@ -259,6 +261,17 @@ def decode_batch_events(cfg, samples_2d, n_threads, lengths=None, flush=False):
         return ev, pay[: _lib().oracle_batch_payload_bytes(h)], secs
     finally:
         _lib().oracle_batch_free(h)
+
+
+def agc_block_model(cfg, samples, block=2048, warm=1024, guess_gain=None):
+    """(blocks, blocks whose warm-started gain differs bitwise from the sequential one, worst samples-to-coalesce):
+    the CPU model of the long-stream path's speculative AGC (oracle_agc_block_model)."""
+    a = np.ascontiguousarray(samples, dtype=np.int16)
+    nb, bad, worst = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    g0 = min(1.0, cfg.agc_gain_min) if guess_gain is None else guess_gain
+    _lib().oracle_agc_block_model(C.byref(cfg), a.ctypes.data, a.size, block, warm, C.c_float(g0), C.byref(nb), C.byref(bad),
+                                  C.byref(worst))
+    return nb.value, bad.value, worst.value
 
 
 class _CpuBurst(C.Structure):

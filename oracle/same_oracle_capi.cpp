@@ -292,6 +292,37 @@ void oracle_batch_copy(void* h, oracle_batch_event* events, uint8_t* payload) {
 }
 void oracle_batch_free(void* h) { delete (OracleBatch*)h; }
 
+// Model of the long-stream path's speculative AGC (sameold_b200/csrc/same_long.cu, kernel B), on the oracle's own
+// DCBlocker and Agc: the unlocked AGC recurrence over `n` samples in blocks of `block` samples, every block after the
+// first warm-started `warm` samples earlier from `guess_gain`.  Counts the blocks whose warm-started gain differs
+// BITWISE from the sequential trajectory at the block start (those the engine would recompute) and measures, per
+// block, how many samples the two trajectories needed to coalesce.  Pins the property the path relies on.
+void oracle_agc_block_model(const oracle_config* c, const int16_t* samples, size_t n, size_t block, size_t warm,
+                            float guess_gain, uint32_t* n_blocks, uint32_t* n_mismatch, uint32_t* worst_coalesce) {
+  Config k = to_config(c);
+  SameReceiver rx(k);
+  std::vector<float> d(n), g(n + 1);
+  for (size_t i = 0; i < n; ++i) d[i] = rx.dc_block.filter((float)samples[i]);
+  Agc agc = rx.agc;
+  g[0] = agc.gain;
+  for (size_t i = 0; i < n; ++i) { (void)agc.input(d[i]); g[i + 1] = agc.gain; }   // g[i] = gain before sample i
+  uint32_t nb = 0, bad = 0, worst = 0;
+  for (size_t sk = block; sk < n; sk += block) {
+    Agc a = rx.agc;
+    a.gain = guess_gain;
+    const size_t w0 = sk - warm;
+    uint32_t coalesced_after = (uint32_t)warm + 1u;
+    for (size_t i = w0; i < sk; ++i) {
+      if (coalesced_after > warm && a.gain == g[i]) coalesced_after = (uint32_t)(i - w0);
+      (void)a.input(d[i]);
+    }
+    nb++;
+    if (a.gain != g[sk]) bad++;
+    else if (coalesced_after <= warm && coalesced_after > worst) worst = coalesced_after;
+  }
+  *n_blocks = nb; *n_mismatch = bad; *worst_coalesce = worst;
+}
+
 // CPU corpus generator for bench.py's reference arm (see synth_cpu.hpp): out[s * stride + n], n < n_samples, for
 // n_streams streams on n_threads host threads.  burst_begin has n_streams + 1 entries (CSR into `bursts`).
 void oracle_synth_generate(int16_t* out, size_t n_streams, size_t stride, size_t n_samples, uint32_t rate,

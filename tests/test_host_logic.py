@@ -44,3 +44,27 @@ def test_bench_stripes_ranks_over_the_device_range():
     for world, ndev in [(2, 8), (4, 8), (3, 8), (5, 8), (2, 3), (6, 7)]:
         got = [bench.device_for_rank(r, world, ndev) for r in range(world)]
         assert len(set(got)) == world and all(0 <= d < ndev for d in got)
+
+
+def test_speculative_agc_blocks_coalesce_bitwise_on_the_corpus_noise():
+    """The long-stream path (same_long.cu) runs the unlocked AGC in blocks that warm up 1024 samples early from a guessed
+    gain and uses a block only if its start gain equals the sequential trajectory bit for bit.  Modelled here on the
+    oracle's own DCBlocker/Agc: on the corpus noise (sigma 3663, samedec limits) every hand-over matches and the
+    trajectories coalesce within a few hundred samples, from the gain the stream starts with as well as from the far
+    clamp; on exact silence the gain runs into its upper clamp and matches too."""
+    from oracle import agc_block_model, synth_cpu
+    from oracle.pyoracle import default_config
+    from sameold_b200 import synth
+    cfg = default_config(22050, samedec=True)
+    plan = synth.plan_stream(900, 22050, 120.0)
+    plan.burst_starts, plan.burst_payloads = [], []            # noise only: the AGC stays unlocked
+    x = synth_cpu([plan], 120 * 22050, 22050, 1)[0]
+    for guess in (None, 0.005, 3.0e-4):
+        nb, bad, worst = agc_block_model(cfg, x, 2048, 1024, guess)
+        assert nb > 1000 and bad == 0, (guess, nb, bad)
+        assert 0 < worst < 700, worst
+    nb, bad, _ = agc_block_model(cfg, np.zeros(30 * 22050, np.int16), 2048, 1024, None)
+    assert bad == 0 and nb > 300
+    # a warm-up that is too short is caught by the bitwise check (that is what the verification is for)
+    nb, bad, _ = agc_block_model(cfg, x, 2048, 64, 0.005)
+    assert bad > nb // 2
