@@ -7,7 +7,7 @@
 //   B  same_long_agc_kernel   the AGC recurrence (agc.rs:72-77) in blocks of 2048 samples, one thread per block.  Block 0
 //                             starts from the stream's true gain; every other block warms up on the 1024 samples before
 //                             it from a guessed gain.  The unlocked AGC map contracts (|1 - |d| bw| per sample), so the
-//                             trajectories coalesce BITWISE within ~300 samples on noise (worst seen 412) — and whether a
+//                             trajectories coalesce BITWISE within ~300 samples on noise (worst seen 481) — and whether a
 //                             block's start gain really equals its predecessor's end gain is CHECKED, bit for bit:
 //      same_long_verify_kernel   first block whose hand-over fails -> end of the range that may be consumed.
 //   C  same_long_mf_kernel    the mark/space matched filters (demod.rs:156-164) at EVERY sample position of that AGC
