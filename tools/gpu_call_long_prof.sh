@@ -15,4 +15,4 @@ synth.DeviceCorpus([plan], rate).generate(buf.data_ptr(), buf.numel(), n)
 rx = sb.SameReceiverBuilder.samedec(rate).build_batch(1)
 rx.submit_device(buf.data_ptr(), n, np.zeros(1, np.uint64), np.array([n], np.uint32)); rx.sync(); print(len(rx.drain()))
 PY
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'same_long' -c 4 -o gpurun_out/r2p_long python /tmp/ncu_job.py > gpurun_out/r2p_ncu.log 2>&1; tail -2 gpurun_out/r2p_ncu.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'same_long' -c 5 -o gpurun_out/r2p_long python /tmp/ncu_job.py > gpurun_out/r2p_ncu.log 2>&1; tail -2 gpurun_out/r2p_ncu.log
