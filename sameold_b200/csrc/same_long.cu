@@ -163,6 +163,38 @@ __global__ void __launch_bounds__(256) same_long_mf_kernel(const __grid_constant
 #define LS_RING 64
 struct LsRec { uint32_t pos; float zero, sym, until, pavg, pinst, ted0; uint32_t pad; };
 
+// Ring counters.  LS_RELEASE_ACQUIRE=1: st.release.cta / ld.acquire.cta, the hand-off the PTX memory model defines (the
+// acquire load is a plain LDS in SASS, the release store a MEMBAR.ALL.CTA + STS).  0: volatile accesses, relying on one
+// thread's shared-memory stores being performed in program order.  Both are bit-exact over 24 h
+// (tests/test_zz_config5_24h.py); profiles/README.md has the A/B.
+#ifndef LS_RELEASE_ACQUIRE
+#define LS_RELEASE_ACQUIRE 1
+#endif
+// The counters are published in batches (the release store's MEMBAR is what costs): T every LS_HEAD_BATCH records and
+// when it finishes, S every LS_TAIL_BATCH records and whenever it has drained the ring.
+#ifndef LS_HEAD_BATCH
+#define LS_HEAD_BATCH 4u
+#endif
+#define LS_TAIL_BATCH 8u
+__device__ __forceinline__ void ls_publish(volatile uint32_t* w, uint32_t v) {
+#if LS_RELEASE_ACQUIRE
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(const_cast<uint32_t*>(w))), "r"(v)
+               : "memory");
+#else
+  *w = v;
+#endif
+}
+__device__ __forceinline__ uint32_t ls_observe(const volatile uint32_t* w) {
+#if LS_RELEASE_ACQUIRE
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(const_cast<uint32_t*>(w)))
+               : "memory");
+  return v;
+#else
+  return *w;
+#endif
+}
+
 __global__ void __launch_bounds__(64) same_long_seq_kernel(const __grid_constant__ SameParams p, const float* __restrict__ soft,
                                                            const float* __restrict__ yfull, const float* __restrict__ gspec,
                                                            const uint32_t pos0, uint32_t* __restrict__ ctrl) {
@@ -223,24 +255,23 @@ __global__ void __launch_bounds__(64) same_long_seq_kernel(const __grid_constant
           cfire = fire_clock(a.until, 0);
           if (have_sym) {
             if (head - tail_seen >= (uint32_t)LS_RING) {                   // ring full as far as T knows: look again, wait for S
-              while (head - (tail_seen = sh_tail) >= (uint32_t)LS_RING) { if (sh_stop) { done = 1; break; } }
+              while (head - (tail_seen = ls_observe(&sh_tail)) >= (uint32_t)LS_RING) { if (sh_stop) { done = 1; break; } }
               if (done) break;
             }
-            // volatile stores: a thread's shared-memory stores are performed in program order, so S, which reads the
-            // head counter first, sees a complete record
+            // the record, then the head counter that publishes it (ls_publish)
             volatile float* q = reinterpret_cast<volatile float*>(&ring[head & (LS_RING - 1)]);
             q[1] = a.ted1; q[2] = a.ted2; q[3] = a.until; q[4] = a.pavg; q[5] = a.pinst; q[6] = a.ted0;
             reinterpret_cast<volatile uint32_t*>(q)[0] = pos;
             head += 1u;
-            sh_head = head;
+            if ((head & (LS_HEAD_BATCH - 1u)) == 0u) ls_publish(&sh_head, head);   // S may lag: it feeds back only by stopping
           }
         }
         if (done) {
           t_final[0] = a.until; t_final[1] = a.pavg; t_final[2] = a.pinst; t_final[3] = a.ted0; t_final[4] = a.ted1;
           t_final[5] = a.ted2; t_final[6] = __uint_as_float(a.tedcnt); t_final[7] = __int_as_float(a.clock);
           t_pos = pos;
-          __threadfence_block();
-          sh_tdone = 1u;
+          ls_publish(&sh_head, head);          // whatever the batching held back
+          ls_publish(&sh_tdone, 1u);
         }
       }
       done = __shfl_sync(0xffffffffu, done, 0);
@@ -249,11 +280,12 @@ __global__ void __launch_bounds__(64) same_long_seq_kernel(const __grid_constant
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (lane == 0) {
     // ================================================ S: symbol stages ================================================
-    uint32_t tail = 0;
+    uint32_t tail = 0, tail_pub = 0;
     while (true) {
-      uint32_t head = sh_head;
+      uint32_t head = ls_observe(&sh_head);
       if (tail == head) {
-        if (sh_tdone) { head = sh_head; if (tail == head) break; }
+        if (tail_pub != tail) { ls_publish(&sh_tail, tail); tail_pub = tail; }   // ring drained: T may be waiting for room
+        if (ls_observe(&sh_tdone)) { head = ls_observe(&sh_head); if (tail == head) break; }
         else continue;
       }
       LsRec r;
@@ -289,14 +321,15 @@ __global__ void __launch_bounds__(64) same_long_seq_kernel(const __grid_constant
       }
       if (quiet) {
         tail += 1u;
-        sh_tail = tail;
+        if ((tail & (LS_TAIL_BATCH - 1u)) == 0u) { ls_publish(&sh_tail, tail); tail_pub = tail; }
         continue;
       }
       a.until = r.until; a.pavg = r.pavg; a.pinst = r.pinst;
       a.ted0 = r.ted0; a.ted1 = r.zero; a.ted2 = r.sym; a.tedcnt = 1u; a.clock = 0;
       symbol_step(a, p, 0u, st, blob, r.zero, r.sym, a.n0 + r.pos);
       tail += 1u;
-      sh_tail = tail;
+      ls_publish(&sh_tail, tail);
+      tail_pub = tail;
       if ((a.flags & FLAG_AGC_LOCKED) || a.tedcnt != 1u) {       // sync found (AGC locked) or end() reset the timing loop
         why = (a.flags & FLAG_AGC_LOCKED) ? 1u : 2u;
         stop_pos = r.pos;
